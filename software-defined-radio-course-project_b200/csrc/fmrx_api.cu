@@ -1,0 +1,948 @@
+// fmrx_api.cu -- the extern "C" boundary (include/fmrx.h): per-operator entry
+// points on host pointers, and the fused multi-capture pipeline.
+//
+// Pipeline scheduling.  A call is cut into chunks of whole blocks.  Three CUDA
+// streams form a software pipeline over chunks, the device-side counterpart of
+// the reference's rf_thread -> queue -> audio_thread hand-off
+// (src/project.cpp:71-80,133-141):
+//     front : [H2D] -> K1 rf+demod -> K2 band-pass pair
+//     pll   : K3 PLL recurrence (the long pole: one dependent chain per capture)
+//     back  : K4 audio -> [D2H]
+// Chunk i+1's front stage and chunk i-1's back stage run under chunk i's PLL.
+// Buffers rotate over kSets sets; the FIR history each stage needs from the
+// previous chunk is kept in small per-capture "tail" arrays owned by the stream
+// that produces the data, and copied in front of the next chunk's buffer.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "fmrx.h"
+#include "fmrx_internal.h"
+
+using namespace fmrx;
+
+namespace {
+
+thread_local char g_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    std::snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ||
+        e == cudaErrorNoKernelImageForDevice)
+        return FMRX_ERR_NO_DEVICE;
+    if (e == cudaErrorMemoryAllocation)
+        return FMRX_ERR_ALLOC;
+    return FMRX_ERR_CUDA;
+}
+
+#define CU(call)                                            \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess)                              \
+            return cuda_fail(e_, #call);                    \
+    } while (0)
+
+// Small RAII device buffer for the operator entry points.
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T *as() { return static_cast<T *>(p); }
+};
+
+PllParams make_pll_params(float freq, float Fs, float scale, float adjust, float bw)
+{
+    // src/filter.cpp:139-143,167 -- float products, then (2*PI)*(double)(freq/Fs)
+    PllParams p;
+    const float cp = 2.666f, ci = 3.555f;
+    p.kp = bw * cp;
+    p.ki = (bw * bw) * ci;
+    const float rho = freq / Fs;
+    p.w = (2.0 * 3.14159265358979323846) * static_cast<double>(rho);
+    p.scale = scale;
+    p.adjust = adjust;
+    return p;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// misc
+// ---------------------------------------------------------------------------
+
+extern "C" const char *fmrx_strerror(int s)
+{
+    switch (s) {
+    case FMRX_OK: return "ok";
+    case FMRX_ERR_ARG: return "invalid argument";
+    case FMRX_ERR_NO_DEVICE: return "no usable CUDA (sm_100) device";
+    case FMRX_ERR_CUDA: return "CUDA runtime error";
+    case FMRX_ERR_ALLOC: return "out of memory";
+    case FMRX_ERR_STATE: return "state blob does not match pipeline";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char *fmrx_last_error(void) { return g_err; }
+extern "C" int fmrx_abi_version(void) { return FMRX_ABI_VERSION; }
+
+extern "C" int fmrx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int fmrx_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr)
+        return FMRX_ERR_ARG;
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_host_free(void *ptr)
+{
+    if (ptr)
+        CU(cudaFreeHost(ptr));
+    return FMRX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// per-operator entry points (host pointers)
+// ---------------------------------------------------------------------------
+
+extern "C" int fmrx_u8_to_f32(const uint8_t *raw, size_t n, float *out)
+{
+    if ((!raw || !out) && n)
+        return FMRX_ERR_ARG;
+    if (n == 0)
+        return FMRX_OK;
+    DevBuf din, dout;
+    CU(din.alloc(n));
+    CU(dout.alloc(n * sizeof(float)));
+    CU(cudaMemcpy(din.p, raw, n, cudaMemcpyHostToDevice));
+    CU(launch_u8_to_f32(din.as<uint8_t>(), n, dout.as<float>(), 0));
+    CU(cudaMemcpy(out, dout.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_resample(float *out, size_t *out_len, float *state, size_t state_len,
+                             const float *in, size_t in_len, const float *coeff, int taps,
+                             int up, int down)
+{
+    if (!out_len || !state || !in || !coeff || taps < 1 || up < 1 || down < 1)
+        return FMRX_ERR_ARG;
+    if (in_len < static_cast<size_t>(taps - 1) || in_len > 0x7fffffffu / static_cast<size_t>(up))
+        return FMRX_ERR_ARG;
+    const int n_in = static_cast<int>(in_len);
+    const int n_out = static_cast<int>(static_cast<long long>(n_in) * up / down);   // src/filter.cpp:77
+    if (n_out && !out)
+        return FMRX_ERR_ARG;
+    DevBuf d_in, d_state, d_coeff, d_out;
+    CU(d_in.alloc(in_len * sizeof(float)));
+    CU(d_state.alloc(state_len * sizeof(float)));
+    CU(d_coeff.alloc(taps * sizeof(float)));
+    CU(d_out.alloc(static_cast<size_t>(n_out) * sizeof(float)));
+    CU(cudaMemcpy(d_in.p, in, in_len * sizeof(float), cudaMemcpyHostToDevice));
+    if (state_len)
+        CU(cudaMemcpy(d_state.p, state, state_len * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_coeff.p, coeff, taps * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_resample(d_out.as<float>(), n_out, d_state.as<float>(), static_cast<int>(state_len),
+                       d_in.as<float>(), n_in, d_coeff.as<float>(), taps, up, down, 0));
+    if (n_out)
+        CU(cudaMemcpy(out, d_out.p, static_cast<size_t>(n_out) * sizeof(float), cudaMemcpyDeviceToHost));
+    else
+        CU(cudaDeviceSynchronize());
+    // src/filter.cpp:95-102: state := last taps-1 inputs (a copy; no arithmetic)
+    std::memmove(state, in + (in_len - (taps - 1)), static_cast<size_t>(taps - 1) * sizeof(float));
+    *out_len = static_cast<size_t>(n_out);
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_fmdemod(float *out, float *prev_i, float *prev_q, const float *i_ds,
+                            const float *q_ds, size_t n)
+{
+    if (!prev_i || !prev_q || ((!out || !i_ds || !q_ds) && n) || n > 0x7fffffffu)
+        return FMRX_ERR_ARG;
+    if (n == 0)
+        return FMRX_OK;
+    DevBuf di, dq, dout;
+    CU(di.alloc(n * sizeof(float)));
+    CU(dq.alloc(n * sizeof(float)));
+    CU(dout.alloc(n * sizeof(float)));
+    CU(cudaMemcpy(di.p, i_ds, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dq.p, q_ds, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_fmdemod(dout.as<float>(), di.as<float>(), dq.as<float>(), static_cast<int>(n),
+                      *prev_i, *prev_q, 0));
+    CU(cudaMemcpy(out, dout.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    *prev_i = i_ds[n - 1];   // src/filter.cpp:130-131 (a copy)
+    *prev_q = q_ds[n - 1];
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_pll(float *inout, size_t n, float freq, float Fs, float nco_scale,
+                        float phase_adjust, float norm_bandwidth, float state[6])
+{
+    if (!state || (!inout && n) || n > 0x7fffffffu)
+        return FMRX_ERR_ARG;
+    if (n == 0)
+        return FMRX_OK;   // the reference would index ncoOut[-1]; nothing to do
+    DevBuf d_x, d_trig, d_state;
+    CU(d_x.alloc(n * sizeof(float)));
+    CU(d_trig.alloc(n * sizeof(float)));
+    CU(d_state.alloc(8 * sizeof(float)));
+    float st8[8] = { state[0], state[1], state[2], state[3], state[4], state[5], 0.0f, 0.0f };
+    CU(cudaMemcpy(d_x.p, inout, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_state.p, st8, sizeof(st8), cudaMemcpyHostToDevice));
+    PllArgs a{};
+    a.pilot = d_x.as<float>();
+    a.pilot_stride = n;
+    a.trig = d_trig.as<float>();
+    a.if_stride = n;
+    a.if_off = 0;
+    a.n_if = static_cast<int>(n);
+    a.state = d_state.as<float>();
+    a.prm = make_pll_params(freq, Fs, nco_scale, phase_adjust, norm_bandwidth);
+    CU(launch_pll(a, 1, 0));
+    CU(launch_nco(d_x.as<float>(), d_trig.as<float>(), n, nco_scale, phase_adjust, 0));
+    CU(cudaMemcpy(inout, d_x.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(st8, d_state.p, sizeof(st8), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 6; i++)
+        state[i] = st8[i];
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_mixer(float *out, const float *a, const float *b, size_t n)
+{
+    if ((!out || !a || !b) && n)
+        return FMRX_ERR_ARG;
+    if (n == 0)
+        return FMRX_OK;
+    DevBuf da, db, dout;
+    CU(da.alloc(n * sizeof(float)));
+    CU(db.alloc(n * sizeof(float)));
+    CU(dout.alloc(n * sizeof(float)));
+    CU(cudaMemcpy(da.p, a, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db.p, b, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_mixer(dout.as<float>(), da.as<float>(), db.as<float>(), n, 0));
+    CU(cudaMemcpy(out, dout.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_lr_extract(float *left, float *right, const float *mono, const float *stereo,
+                               size_t n)
+{
+    if ((!left || !right || !mono || !stereo) && n)
+        return FMRX_ERR_ARG;
+    if (n == 0)
+        return FMRX_OK;
+    DevBuf dm, ds, dl, dr;
+    CU(dm.alloc(n * sizeof(float)));
+    CU(ds.alloc(n * sizeof(float)));
+    CU(dl.alloc(n * sizeof(float)));
+    CU(dr.alloc(n * sizeof(float)));
+    CU(cudaMemcpy(dm.p, mono, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ds.p, stereo, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_lr_extract(dl.as<float>(), dr.as<float>(), dm.as<float>(), ds.as<float>(), n, 0));
+    CU(cudaMemcpy(left, dl.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(right, dr.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_pcm_pack(int16_t *pcm, const float *left, const float *right, size_t n)
+{
+    if ((!pcm || !left || !right) && n)
+        return FMRX_ERR_ARG;
+    if (n == 0)
+        return FMRX_OK;
+    DevBuf dl, dr, dp;
+    CU(dl.alloc(n * sizeof(float)));
+    CU(dr.alloc(n * sizeof(float)));
+    CU(dp.alloc(2 * n * sizeof(int16_t)));
+    CU(cudaMemcpy(dl.p, left, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dr.p, right, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_pcm_pack(dp.as<int16_t>(), dl.as<float>(), dr.as<float>(), n, 0));
+    CU(cudaMemcpy(pcm, dp.p, 2 * n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    return FMRX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fused pipeline
+// ---------------------------------------------------------------------------
+
+namespace {
+constexpr int kSets = 3;
+constexpr uint32_t kStateMagic = 0x58524d46u;   // "FMRX"
+
+struct StateHeader {
+    uint32_t magic, mode, taps, hist_if, hist_pairs, reserved;
+    int64_t blocks_done;
+};
+
+struct BufferSet {
+    uint8_t *iq = nullptr;      // host-path staging: [C][chunk_blocks*block_size]
+    float *demod = nullptr;     // [C][H + chunk_if]
+    float *chan = nullptr;      // [C][H + chunk_if]
+    float *trig = nullptr;      // [C][H + chunk_if]
+    float *pilot = nullptr;     // [C][chunk_if]
+    int16_t *pcm = nullptr;     // host-path staging: [C][chunk_blocks*2*audio_per_block]
+    cudaEvent_t front_done = nullptr, pll_done = nullptr, free_ev = nullptr;
+    bool free_pending = false;  // free_ev has been recorded at least once
+};
+}  // namespace
+
+struct fmrx_pipeline {
+    fmrx_mode_info mi{};
+    int C = 0, device = 0;
+    int chunk_blocks = 0;       // blocks per chunk
+    int chunk_if = 0;           // IF samples per chunk per capture
+    int H = 0;                  // IF history kept in front of every IF-rate buffer
+    int hist_pairs = 0;         // IQ pairs of history for K1
+    size_t if_stride = 0;       // H + chunk_if
+    bool keep_stages = false, timing = false;
+    PllParams pll_prm{};
+
+    float *d_rf_taps = nullptr, *d_pilot_taps = nullptr, *d_chan_taps = nullptr, *d_audio_pm = nullptr;
+    uint8_t *d_hist_iq = nullptr;                         // [C][2*hist_pairs]
+    float *d_tail_demod = nullptr, *d_tail_chan = nullptr, *d_tail_trig = nullptr;   // [C][H]
+    float *d_pll_state = nullptr;                         // [C][8]
+    BufferSet sets[kSets];
+    cudaStream_t s_front = nullptr, s_pll = nullptr, s_back = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    long long blocks_done = 0;
+    long long chunk_counter = 0;
+    uint64_t launches = 0;
+
+    // keep_stages storage (sized for the last call)
+    float *d_stage[FMRX_STAGE_COUNT] = {};
+    size_t stage_if_len = 0, stage_au_len = 0;
+
+    // timing
+    std::vector<cudaEvent_t> tev;     // per chunk: 8 events
+    float last_ms[4] = { 0, 0, 0, 0 };
+};
+
+namespace {
+
+void free_pipeline(fmrx_pipeline *p)
+{
+    if (!p)
+        return;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    auto F = [](void *q) { if (q) cudaFree(q); };
+    F(p->d_rf_taps); F(p->d_pilot_taps); F(p->d_chan_taps); F(p->d_audio_pm);
+    F(p->d_hist_iq); F(p->d_tail_demod); F(p->d_tail_chan); F(p->d_tail_trig); F(p->d_pll_state);
+    for (auto &s : p->sets) {
+        F(s.iq); F(s.demod); F(s.chan); F(s.trig); F(s.pilot); F(s.pcm);
+        if (s.front_done) cudaEventDestroy(s.front_done);
+        if (s.pll_done) cudaEventDestroy(s.pll_done);
+        if (s.free_ev) cudaEventDestroy(s.free_ev);
+    }
+    for (auto &q : p->d_stage) F(q);
+    for (auto e : p->tev) cudaEventDestroy(e);
+    if (p->ev_in) cudaEventDestroy(p->ev_in);
+    if (p->ev_out) cudaEventDestroy(p->ev_out);
+    if (p->s_front) cudaStreamDestroy(p->s_front);
+    if (p->s_pll) cudaStreamDestroy(p->s_pll);
+    if (p->s_back) cudaStreamDestroy(p->s_back);
+    delete p;
+}
+
+int reset_state(fmrx_pipeline *p)
+{
+    const size_t C = p->C;
+    CU(cudaMemset(p->d_hist_iq, 0x80, C * 2 * p->hist_pairs));      // u8 128 == 0.0f
+    CU(cudaMemset(p->d_tail_demod, 0, C * p->H * sizeof(float)));
+    CU(cudaMemset(p->d_tail_chan, 0, C * p->H * sizeof(float)));
+    CU(cudaMemset(p->d_tail_trig, 0, C * p->H * sizeof(float)));
+    // src/project.cpp:106-111
+    std::vector<float> st(C * 8, 0.0f);
+    for (size_t c = 0; c < C; c++) {
+        st[8 * c + 2] = 1.0f;   // feedbackI
+        st[8 * c + 4] = 1.0f;   // ncoOut_state
+    }
+    CU(cudaMemcpy(p->d_pll_state, st.data(), st.size() * sizeof(float), cudaMemcpyHostToDevice));
+    p->blocks_done = 0;
+    return FMRX_OK;
+}
+
+template <class T> cudaError_t dalloc(T **q, size_t count)
+{
+    return cudaMalloc(reinterpret_cast<void **>(q), (count ? count : 1) * sizeof(T));
+}
+
+int create_impl(fmrx_pipeline *p, const fmrx_config *cfg)
+{
+    const fmrx_mode_info &mi = p->mi;
+    const int T = mi.taps, U = mi.audio_interp, D = mi.audio_decim;
+    p->C = cfg->n_captures;
+    p->keep_stages = cfg->keep_stages != 0;
+    const size_t C = p->C;
+
+    // history: band-pass needs T-1; the audio stage needs T-1 + 5 delayed frames
+    const int delay_if = (kMonoDelay * D + U - 1) / U;
+    p->H = ((T + delay_if + 8 + 31) / 32) * 32;
+    p->hist_pairs = T - 1 + mi.rf_decim;
+    if (mi.if_per_block < p->H || mi.block_size / 2 < p->hist_pairs)
+        return FMRX_ERR_ARG;
+
+    int cb = cfg->chunk_blocks;
+    if (cb <= 0) {
+        // aim at ~32 MiB per IF-rate array per chunk
+        const size_t target_if = (32u << 20) / sizeof(float) / C;
+        cb = static_cast<int>(std::max<size_t>(1, target_if / mi.if_per_block));
+        cb = std::min(cb, 4096);
+    }
+    p->chunk_blocks = cb;
+    p->chunk_if = cb * mi.if_per_block;
+    p->if_stride = static_cast<size_t>(p->H) + p->chunk_if;
+
+    // filters (src/project.cpp:37,97,104,117)
+    std::vector<float> rf(T), pil(T), ch(T), au(mi.audio_taps), au_pm(mi.audio_taps);
+    fmrx_impulse_response_lpf(rf.data(), static_cast<float>(mi.rf_fs), 100000.0f, T, 1);
+    fmrx_impulse_response_bpf(ch.data(), static_cast<float>(mi.bp_fs), 22000.0f, 54000.0f, T);
+    fmrx_impulse_response_bpf(pil.data(), static_cast<float>(mi.bp_fs), 18500.0f, 19500.0f, T);
+    fmrx_impulse_response_lpf(au.data(), static_cast<float>(mi.if_fs), 16000.0f, mi.audio_taps, U);
+    for (int ph = 0; ph < U; ph++)
+        for (int t = 0; t < T; t++)
+            au_pm[static_cast<size_t>(ph) * T + t] = au[ph + static_cast<size_t>(t) * U];
+    // src/project.cpp:166: PLL(19000, if_fs, 2, 0, 0.01)
+    p->pll_prm = make_pll_params(19000.0f, static_cast<float>(mi.if_fs), 2.0f, 0.0f, 0.01f);
+
+    CU(dalloc(&p->d_rf_taps, T));
+    CU(dalloc(&p->d_pilot_taps, T));
+    CU(dalloc(&p->d_chan_taps, T));
+    CU(dalloc(&p->d_audio_pm, au_pm.size()));
+    CU(cudaMemcpy(p->d_rf_taps, rf.data(), T * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_pilot_taps, pil.data(), T * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_chan_taps, ch.data(), T * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_audio_pm, au_pm.data(), au_pm.size() * sizeof(float), cudaMemcpyHostToDevice));
+
+    CU(dalloc(&p->d_hist_iq, C * 2 * p->hist_pairs));
+    CU(dalloc(&p->d_tail_demod, C * p->H));
+    CU(dalloc(&p->d_tail_chan, C * p->H));
+    CU(dalloc(&p->d_tail_trig, C * p->H));
+    CU(dalloc(&p->d_pll_state, C * 8));
+    for (auto &s : p->sets) {
+        CU(dalloc(&s.demod, C * p->if_stride));
+        CU(dalloc(&s.chan, C * p->if_stride));
+        CU(dalloc(&s.trig, C * p->if_stride));
+        CU(dalloc(&s.pilot, C * static_cast<size_t>(p->chunk_if)));
+        CU(cudaEventCreateWithFlags(&s.front_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.pll_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.free_ev, cudaEventDisableTiming));
+    }
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&p->s_front, cudaStreamNonBlocking, lo));
+    CU(cudaStreamCreateWithPriority(&p->s_pll, cudaStreamNonBlocking, hi));   // the long pole first
+    CU(cudaStreamCreateWithPriority(&p->s_back, cudaStreamNonBlocking, lo));
+    CU(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
+    return reset_state(p);
+}
+
+// Lazily allocated staging for the host-pointer path.
+int ensure_host_staging(fmrx_pipeline *p)
+{
+    const size_t C = p->C;
+    for (auto &s : p->sets) {
+        if (!s.iq)
+            CU(dalloc(&s.iq, C * static_cast<size_t>(p->chunk_blocks) * p->mi.block_size));
+        if (!s.pcm)
+            CU(dalloc(&s.pcm, C * static_cast<size_t>(p->chunk_blocks) * 2 * p->mi.audio_per_block));
+    }
+    return FMRX_OK;
+}
+
+int ensure_stage_storage(fmrx_pipeline *p, size_t n_blocks)
+{
+    const size_t if_len = n_blocks * p->mi.if_per_block, au_len = n_blocks * p->mi.audio_per_block;
+    if (if_len <= p->stage_if_len && au_len <= p->stage_au_len && p->d_stage[0]) {
+        p->stage_if_len = if_len;   // logical length of the last call
+        p->stage_au_len = au_len;
+        return FMRX_OK;
+    }
+    for (auto &q : p->d_stage) {
+        if (q) cudaFree(q);
+        q = nullptr;
+    }
+    for (int s = 0; s < FMRX_STAGE_COUNT; s++) {
+        const size_t len = (s >= FMRX_STAGE_MONO) ? au_len : if_len;
+        CU(dalloc(&p->d_stage[s], static_cast<size_t>(p->C) * len));
+    }
+    p->stage_if_len = if_len;
+    p->stage_au_len = au_len;
+    return FMRX_OK;
+}
+
+// Copy `rows` rows of `width` bytes between pitched device arrays.
+cudaError_t copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width,
+                   size_t rows, cudaStream_t s, cudaMemcpyKind kind = cudaMemcpyDeviceToDevice)
+{
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, s);
+}
+
+// The chunk loop shared by the host- and device-pointer entry points.
+int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, int16_t *pcm,
+        size_t pcm_stride, bool host_io, cudaStream_t user)
+{
+    const fmrx_mode_info &mi = p->mi;
+    const int C = p->C, T = mi.taps, H = p->H;
+    const size_t fH = static_cast<size_t>(H) * sizeof(float);
+    const size_t if_pitch = p->if_stride * sizeof(float);
+
+    if (host_io) {
+        const int rc = ensure_host_staging(p);
+        if (rc != FMRX_OK) return rc;
+    }
+    if (p->keep_stages) {
+        const int rc = ensure_stage_storage(p, n_blocks);
+        if (rc != FMRX_OK) return rc;
+    }
+    if (!host_io) {
+        // order after the caller's stream
+        CU(cudaEventRecord(p->ev_in, user));
+        CU(cudaStreamWaitEvent(p->s_front, p->ev_in, 0));
+        CU(cudaStreamWaitEvent(p->s_pll, p->ev_in, 0));
+        CU(cudaStreamWaitEvent(p->s_back, p->ev_in, 0));
+    }
+
+    const size_t n_chunks = (n_blocks + p->chunk_blocks - 1) / p->chunk_blocks;
+    if (p->timing) {
+        while (p->tev.size() < 8 * n_chunks) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            p->tev.push_back(e);
+        }
+    }
+
+    for (size_t ci = 0; ci < n_chunks; ci++) {
+        const size_t b0 = ci * p->chunk_blocks;
+        const int nb = static_cast<int>(std::min<size_t>(p->chunk_blocks, n_blocks - b0));
+        const int n_if = nb * mi.if_per_block;
+        const size_t chunk_bytes = static_cast<size_t>(nb) * mi.block_size;
+        const size_t chunk_pcm = static_cast<size_t>(nb) * 2 * mi.audio_per_block;
+        BufferSet &S = p->sets[p->chunk_counter % kSets];
+        cudaEvent_t *te = p->timing ? &p->tev[8 * ci] : nullptr;
+
+        // ---------------- front: [H2D] K1 K2 ----------------
+        if (S.free_pending)
+            CU(cudaStreamWaitEvent(p->s_front, S.free_ev, 0));
+        const uint8_t *iq_dev;
+        size_t iq_dev_stride;
+        if (host_io) {
+            iq_dev = S.iq;
+            iq_dev_stride = static_cast<size_t>(p->chunk_blocks) * mi.block_size;
+            CU(copy2d(S.iq, iq_dev_stride, iq + b0 * mi.block_size, iq_stride, chunk_bytes, C,
+                      p->s_front, cudaMemcpyHostToDevice));
+        } else {
+            iq_dev = iq + b0 * mi.block_size;
+            iq_dev_stride = iq_stride;
+        }
+        if (te) CU(cudaEventRecord(te[0], p->s_front));
+        CU(copy2d(S.demod, if_pitch, p->d_tail_demod, fH, fH, C, p->s_front));
+        CU(copy2d(S.chan, if_pitch, p->d_tail_chan, fH, fH, C, p->s_front));
+        {
+            RfDemodArgs a{};
+            a.iq = iq_dev;
+            a.iq_stride = iq_dev_stride;
+            a.hist = p->d_hist_iq;
+            a.hist_pairs = p->hist_pairs;
+            a.taps = p->d_rf_taps;
+            a.T = T;
+            a.decim = mi.rf_decim;
+            a.n_if = n_if;
+            a.demod = S.demod;
+            a.if_stride = p->if_stride;
+            a.if_off = H;
+            if (p->keep_stages) {
+                a.i_ds = p->d_stage[FMRX_STAGE_I_DS];
+                a.q_ds = p->d_stage[FMRX_STAGE_Q_DS];
+                a.stage_stride = p->stage_if_len;
+                a.stage_off = b0 * mi.if_per_block;
+            }
+            CU(launch_rf_demod(a, C, p->s_front));
+            p->launches++;
+        }
+        if (te) CU(cudaEventRecord(te[1], p->s_front));
+        // IQ history for the next chunk: the last hist_pairs pairs of this chunk
+        CU(copy2d(p->d_hist_iq, 2 * static_cast<size_t>(p->hist_pairs),
+                  iq_dev + chunk_bytes - 2 * static_cast<size_t>(p->hist_pairs), iq_dev_stride,
+                  2 * static_cast<size_t>(p->hist_pairs), C, p->s_front));
+        {
+            BandpassArgs a{};
+            a.demod = S.demod;
+            a.if_stride = p->if_stride;
+            a.if_off = H;
+            a.taps_pilot = p->d_pilot_taps;
+            a.taps_chan = p->d_chan_taps;
+            a.T = T;
+            a.n_if = n_if;
+            a.pilot = S.pilot;
+            a.pilot_stride = p->chunk_if;
+            a.chan = S.chan;
+            CU(launch_bandpass_pair(a, C, p->s_front));
+            p->launches++;
+        }
+        if (te) CU(cudaEventRecord(te[2], p->s_front));
+        // tails for the next chunk's front stage
+        CU(copy2d(p->d_tail_demod, fH, S.demod + n_if, if_pitch, fH, C, p->s_front));
+        CU(copy2d(p->d_tail_chan, fH, S.chan + n_if, if_pitch, fH, C, p->s_front));
+        CU(cudaEventRecord(S.front_done, p->s_front));
+
+        // ---------------- pll: K3 ----------------
+        CU(cudaStreamWaitEvent(p->s_pll, S.front_done, 0));
+        CU(copy2d(S.trig, if_pitch, p->d_tail_trig, fH, fH, C, p->s_pll));
+        if (te) CU(cudaEventRecord(te[3], p->s_pll));
+        {
+            PllArgs a{};
+            a.pilot = S.pilot;
+            a.pilot_stride = p->chunk_if;
+            a.trig = S.trig;
+            a.if_stride = p->if_stride;
+            a.if_off = H;
+            a.n_if = n_if;
+            a.state = p->d_pll_state;
+            a.prm = p->pll_prm;
+            CU(launch_pll(a, C, p->s_pll));
+            p->launches++;
+        }
+        if (te) CU(cudaEventRecord(te[4], p->s_pll));
+        CU(copy2d(p->d_tail_trig, fH, S.trig + n_if, if_pitch, fH, C, p->s_pll));
+        CU(cudaEventRecord(S.pll_done, p->s_pll));
+
+        // ---------------- back: K4 [D2H] ----------------
+        CU(cudaStreamWaitEvent(p->s_back, S.pll_done, 0));
+        if (te) CU(cudaEventRecord(te[5], p->s_back));
+        {
+            AudioArgs a{};
+            a.demod = S.demod;
+            a.chan = S.chan;
+            a.trig = S.trig;
+            a.if_stride = p->if_stride;
+            a.if_off = H;
+            a.coef_pm = p->d_audio_pm;
+            a.T = T;
+            a.U = mi.audio_interp;
+            a.D = mi.audio_decim;
+            a.if_per_block = mi.if_per_block;
+            a.audio_per_block = mi.audio_per_block;
+            a.n_blocks = nb;
+            a.first_block = p->blocks_done;
+            a.scale = p->pll_prm.scale;
+            a.adjust = p->pll_prm.adjust;
+            if (host_io) {
+                a.pcm = S.pcm;
+                a.pcm_stride = static_cast<size_t>(p->chunk_blocks) * 2 * mi.audio_per_block;
+            } else {
+                a.pcm = pcm + b0 * 2 * mi.audio_per_block;
+                a.pcm_stride = pcm_stride;
+            }
+            if (p->keep_stages) {
+                a.nco = p->d_stage[FMRX_STAGE_NCO];
+                a.mixer = p->d_stage[FMRX_STAGE_MIXER];
+                a.if_stage_stride = p->stage_if_len;
+                a.if_stage_off = b0 * mi.if_per_block;
+                a.mono = p->d_stage[FMRX_STAGE_MONO];
+                a.mono_shift = p->d_stage[FMRX_STAGE_MONO_SHIFT];
+                a.stereo = p->d_stage[FMRX_STAGE_STEREO];
+                a.left = p->d_stage[FMRX_STAGE_LEFT];
+                a.right = p->d_stage[FMRX_STAGE_RIGHT];
+                a.au_stage_stride = p->stage_au_len;
+                a.au_stage_off = b0 * mi.audio_per_block;
+            }
+            CU(launch_audio(a, C, p->s_back));
+            p->launches++;
+        }
+        if (te) CU(cudaEventRecord(te[6], p->s_back));
+        if (p->keep_stages) {
+            const size_t w = static_cast<size_t>(n_if) * sizeof(float);
+            const size_t dp = p->stage_if_len * sizeof(float);
+            const size_t off = b0 * mi.if_per_block;
+            CU(copy2d(p->d_stage[FMRX_STAGE_DEMOD] + off, dp, S.demod + H, if_pitch, w, C, p->s_back));
+            CU(copy2d(p->d_stage[FMRX_STAGE_CHAN] + off, dp, S.chan + H, if_pitch, w, C, p->s_back));
+            CU(copy2d(p->d_stage[FMRX_STAGE_TRIG] + off, dp, S.trig + H, if_pitch, w, C, p->s_back));
+            CU(copy2d(p->d_stage[FMRX_STAGE_PILOT] + off, dp, S.pilot,
+                      static_cast<size_t>(p->chunk_if) * sizeof(float), w, C, p->s_back));
+        }
+        if (host_io)
+            CU(copy2d(pcm + b0 * 2 * mi.audio_per_block, pcm_stride * sizeof(int16_t), S.pcm,
+                      static_cast<size_t>(p->chunk_blocks) * 2 * mi.audio_per_block * sizeof(int16_t),
+                      chunk_pcm * sizeof(int16_t), C, p->s_back, cudaMemcpyDeviceToHost));
+        if (te) CU(cudaEventRecord(te[7], p->s_back));
+        CU(cudaEventRecord(S.free_ev, p->s_back));
+        S.free_pending = true;
+
+        p->blocks_done += nb;
+        p->chunk_counter++;
+    }
+
+    if (host_io) {
+        CU(cudaStreamSynchronize(p->s_back));
+        CU(cudaStreamSynchronize(p->s_pll));
+        CU(cudaStreamSynchronize(p->s_front));
+    } else {
+        CU(cudaEventRecord(p->ev_out, p->s_back));
+        CU(cudaStreamWaitEvent(user, p->ev_out, 0));
+        CU(cudaEventRecord(p->ev_out, p->s_pll));
+        CU(cudaStreamWaitEvent(user, p->ev_out, 0));
+        CU(cudaEventRecord(p->ev_out, p->s_front));
+        CU(cudaStreamWaitEvent(user, p->ev_out, 0));
+    }
+    if (p->timing) {
+        CU(cudaStreamSynchronize(p->s_back));
+        CU(cudaStreamSynchronize(p->s_front));
+        float acc[4] = { 0, 0, 0, 0 };
+        for (size_t ci = 0; ci < n_chunks; ci++) {
+            cudaEvent_t *te = &p->tev[8 * ci];
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, te[0], te[1])); acc[0] += ms;
+            CU(cudaEventElapsedTime(&ms, te[1], te[2])); acc[1] += ms;
+            CU(cudaEventElapsedTime(&ms, te[3], te[4])); acc[2] += ms;
+            CU(cudaEventElapsedTime(&ms, te[5], te[6])); acc[3] += ms;
+        }
+        std::memcpy(p->last_ms, acc, sizeof(acc));
+    }
+    return FMRX_OK;
+}
+
+int check_io(const fmrx_pipeline *p, const void *iq, size_t iq_stride, size_t n_blocks,
+             const void *pcm, size_t pcm_stride)
+{
+    if (!p || !iq || !pcm)
+        return FMRX_ERR_ARG;
+    const size_t need_iq = n_blocks * p->mi.block_size;
+    const size_t need_pcm = n_blocks * 2 * p->mi.audio_per_block;
+    if (p->C > 1 && (iq_stride < need_iq || pcm_stride < need_pcm))
+        return FMRX_ERR_ARG;
+    // K1 reads IQ pairs as 16-bit words, K4 writes R,L frames as 32-bit words
+    if ((reinterpret_cast<uintptr_t>(iq) | iq_stride) & 1u)
+        return FMRX_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(pcm) & 3u) || (pcm_stride & 1u))
+        return FMRX_ERR_ARG;
+    return FMRX_OK;
+}
+
+}  // namespace
+
+extern "C" int fmrx_create(fmrx_pipeline **out, const fmrx_config *cfg)
+{
+    if (!out || !cfg || cfg->n_captures < 1)
+        return FMRX_ERR_ARG;
+    for (int r : cfg->reserved)
+        if (r != 0)
+            return FMRX_ERR_ARG;
+    *out = nullptr;
+    fmrx_mode_info mi;
+    if (fmrx_mode_table(cfg->mode, cfg->taps, &mi) != FMRX_OK)
+        return FMRX_ERR_ARG;
+    if (fmrx_device_count() < 1) {
+        std::snprintf(g_err, sizeof(g_err), "no CUDA device");
+        return FMRX_ERR_NO_DEVICE;
+    }
+    int dev = cfg->device;
+    if (dev < 0)
+        CU(cudaGetDevice(&dev));
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        std::snprintf(g_err, sizeof(g_err), "device %d is sm_%d%d; this library is sm_100a only", dev,
+                      prop.major, prop.minor);
+        return FMRX_ERR_NO_DEVICE;
+    }
+    fmrx_pipeline *p = new (std::nothrow) fmrx_pipeline();
+    if (!p)
+        return FMRX_ERR_ALLOC;
+    p->mi = mi;
+    p->device = dev;
+    const int rc = create_impl(p, cfg);
+    if (rc != FMRX_OK) {
+        free_pipeline(p);
+        return rc;
+    }
+    *out = p;
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_destroy(fmrx_pipeline *p)
+{
+    free_pipeline(p);
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_info(const fmrx_pipeline *p, fmrx_mode_info *out)
+{
+    if (!p || !out)
+        return FMRX_ERR_ARG;
+    *out = p->mi;
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_reset(fmrx_pipeline *p)
+{
+    if (!p)
+        return FMRX_ERR_ARG;
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    return reset_state(p);
+}
+
+extern "C" int fmrx_process(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks,
+                            int16_t *pcm, size_t pcm_stride)
+{
+    if (n_blocks == 0)
+        return p ? FMRX_OK : FMRX_ERR_ARG;
+    const int rc = check_io(p, iq, iq_stride, n_blocks, pcm, pcm_stride);
+    if (rc != FMRX_OK)
+        return rc;
+    CU(cudaSetDevice(p->device));
+    return run(p, iq, iq_stride, n_blocks, pcm, pcm_stride, true, nullptr);
+}
+
+extern "C" int fmrx_process_device(fmrx_pipeline *p, const uint8_t *iq_dev, size_t iq_stride,
+                                   size_t n_blocks, int16_t *pcm_dev, size_t pcm_stride, void *stream)
+{
+    if (n_blocks == 0)
+        return p ? FMRX_OK : FMRX_ERR_ARG;
+    const int rc = check_io(p, iq_dev, iq_stride, n_blocks, pcm_dev, pcm_stride);
+    if (rc != FMRX_OK)
+        return rc;
+    CU(cudaSetDevice(p->device));
+    return run(p, iq_dev, iq_stride, n_blocks, pcm_dev, pcm_stride, false,
+               static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fmrx_read_stage(fmrx_pipeline *p, int stage, int capture, float *out, size_t n,
+                               size_t *n_out)
+{
+    if (!p || stage < 0 || stage >= FMRX_STAGE_COUNT || capture < 0 || capture >= p->C || !out)
+        return FMRX_ERR_ARG;
+    if (!p->keep_stages || !p->d_stage[stage])
+        return FMRX_ERR_STATE;
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    const size_t len = (stage >= FMRX_STAGE_MONO) ? p->stage_au_len : p->stage_if_len;
+    const size_t k = std::min(n, len);
+    if (k)
+        CU(cudaMemcpy(out, p->d_stage[stage] + static_cast<size_t>(capture) * len, k * sizeof(float),
+                      cudaMemcpyDeviceToHost));
+    if (n_out)
+        *n_out = k;
+    return FMRX_OK;
+}
+
+extern "C" size_t fmrx_state_size(const fmrx_pipeline *p)
+{
+    if (!p)
+        return 0;
+    const size_t iq = (2 * static_cast<size_t>(p->hist_pairs) + 3) & ~static_cast<size_t>(3);
+    return sizeof(StateHeader) + iq + 3 * static_cast<size_t>(p->H) * sizeof(float) + 8 * sizeof(float);
+}
+
+extern "C" int fmrx_get_state(fmrx_pipeline *p, int capture, void *blob, size_t blob_size)
+{
+    if (!p || !blob || capture < 0 || capture >= p->C || blob_size < fmrx_state_size(p))
+        return FMRX_ERR_ARG;
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    uint8_t *b = static_cast<uint8_t *>(blob);
+    std::memset(b, 0, fmrx_state_size(p));
+    StateHeader h{ kStateMagic, static_cast<uint32_t>(p->mi.mode), static_cast<uint32_t>(p->mi.taps),
+                   static_cast<uint32_t>(p->H), static_cast<uint32_t>(p->hist_pairs), 0, p->blocks_done };
+    std::memcpy(b, &h, sizeof(h));
+    b += sizeof(h);
+    const size_t iqb = 2 * static_cast<size_t>(p->hist_pairs);
+    CU(cudaMemcpy(b, p->d_hist_iq + capture * iqb, iqb, cudaMemcpyDeviceToHost));
+    b += (iqb + 3) & ~static_cast<size_t>(3);
+    const size_t fH = static_cast<size_t>(p->H) * sizeof(float);
+    CU(cudaMemcpy(b, p->d_tail_demod + static_cast<size_t>(capture) * p->H, fH, cudaMemcpyDeviceToHost));
+    b += fH;
+    CU(cudaMemcpy(b, p->d_tail_chan + static_cast<size_t>(capture) * p->H, fH, cudaMemcpyDeviceToHost));
+    b += fH;
+    CU(cudaMemcpy(b, p->d_tail_trig + static_cast<size_t>(capture) * p->H, fH, cudaMemcpyDeviceToHost));
+    b += fH;
+    CU(cudaMemcpy(b, p->d_pll_state + 8 * static_cast<size_t>(capture), 8 * sizeof(float),
+                  cudaMemcpyDeviceToHost));
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_set_state(fmrx_pipeline *p, int capture, const void *blob, size_t blob_size,
+                              int parts)
+{
+    if (!p || !blob || capture < 0 || capture >= p->C || blob_size < fmrx_state_size(p) ||
+        !(parts & FMRX_STATE_ALL))
+        return FMRX_ERR_ARG;
+    const uint8_t *b = static_cast<const uint8_t *>(blob);
+    StateHeader h;
+    std::memcpy(&h, b, sizeof(h));
+    if (h.magic != kStateMagic || h.mode != static_cast<uint32_t>(p->mi.mode) ||
+        h.taps != static_cast<uint32_t>(p->mi.taps) || h.hist_if != static_cast<uint32_t>(p->H) ||
+        h.hist_pairs != static_cast<uint32_t>(p->hist_pairs))
+        return FMRX_ERR_STATE;
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    b += sizeof(h);
+    const size_t iqb = 2 * static_cast<size_t>(p->hist_pairs);
+    const size_t fH = static_cast<size_t>(p->H) * sizeof(float);
+    const uint8_t *b_iq = b;
+    const uint8_t *b_demod = b_iq + ((iqb + 3) & ~static_cast<size_t>(3));
+    const uint8_t *b_chan = b_demod + fH;
+    const uint8_t *b_trig = b_chan + fH;
+    const uint8_t *b_pll = b_trig + fH;
+    if (parts & FMRX_STATE_FEEDFORWARD) {
+        CU(cudaMemcpy(p->d_hist_iq + capture * iqb, b_iq, iqb, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(p->d_tail_demod + static_cast<size_t>(capture) * p->H, b_demod, fH,
+                      cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(p->d_tail_chan + static_cast<size_t>(capture) * p->H, b_chan, fH,
+                      cudaMemcpyHostToDevice));
+    }
+    if (parts & FMRX_STATE_PLL) {
+        CU(cudaMemcpy(p->d_tail_trig + static_cast<size_t>(capture) * p->H, b_trig, fH,
+                      cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(p->d_pll_state + 8 * static_cast<size_t>(capture), b_pll, 8 * sizeof(float),
+                      cudaMemcpyHostToDevice));
+        p->blocks_done = h.blocks_done;
+    }
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_get_pll_state(fmrx_pipeline *p, int capture, float out[6])
+{
+    if (!p || !out || capture < 0 || capture >= p->C)
+        return FMRX_ERR_ARG;
+    CU(cudaSetDevice(p->device));
+    CU(cudaDeviceSynchronize());
+    float st[8];
+    CU(cudaMemcpy(st, p->d_pll_state + 8 * static_cast<size_t>(capture), sizeof(st),
+                  cudaMemcpyDeviceToHost));
+    std::memcpy(out, st, 6 * sizeof(float));
+    return FMRX_OK;
+}
+
+extern "C" uint64_t fmrx_kernel_launches(const fmrx_pipeline *p) { return p ? p->launches : 0; }
+
+extern "C" int fmrx_set_timing(fmrx_pipeline *p, int enable)
+{
+    if (!p)
+        return FMRX_ERR_ARG;
+    p->timing = enable != 0;
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_last_timing(fmrx_pipeline *p, float out_ms[4])
+{
+    if (!p || !out_ms)
+        return FMRX_ERR_ARG;
+    std::memcpy(out_ms, p->last_ms, sizeof(p->last_ms));
+    return FMRX_OK;
+}

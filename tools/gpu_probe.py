@@ -1,0 +1,47 @@
+"""Quick device-side timing probe (not the benchmark): per-kernel-family times of the
+fused pipeline on synthetic captures resident in HBM."""
+import argparse, importlib, json, sys, time
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import numpy as np
+import torch
+
+pkg = importlib.import_module("software-defined-radio-course-project_b200")
+fm = pkg.binding
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--captures", type=int, default=64)
+ap.add_argument("--seconds", type=float, default=2.0)
+ap.add_argument("--mode", type=int, default=0)
+ap.add_argument("--taps", type=int, default=51)
+ap.add_argument("--chunk", type=int, default=0)
+ap.add_argument("--reps", type=int, default=3)
+a = ap.parse_args()
+
+info = fm.mode_table(a.mode, a.taps)
+nb = max(1, int(a.seconds * info.rf_fs * 2 / info.block_size))
+C = a.captures
+one = torch.from_numpy(pkg.synth.synth_iq(nb * info.block_size // 2, info.rf_fs, seed=0)).cuda()
+iq = one.unsqueeze(0).repeat(C, 1).contiguous()
+pcm = torch.zeros((C, nb * 2 * info.audio_per_block), dtype=torch.int16, device="cuda")
+p = fm.Pipeline(a.mode, a.taps, C, chunk_blocks=a.chunk)
+p.set_timing(True)
+s = torch.cuda.current_stream()
+for r in range(a.reps):
+    p.reset()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    p.process_device(iq.data_ptr(), iq.stride(0), nb, pcm.data_ptr(), pcm.stride(0), s.cuda_stream)
+    e1.record(s)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = p.last_timing()
+    n_if = nb * info.if_per_block
+    out = {"mode": a.mode, "taps": a.taps, "captures": C, "blocks": nb, "total_ms": ms,
+           "wall_ms": (time.perf_counter() - t0) * 1e3,
+           "iq_msps": C * nb * info.block_size / 2 / ms / 1e3,
+           "pll_ns_per_sample": t["pll_ms"] * 1e6 / n_if, **t}
+    print(json.dumps(out))
