@@ -12,6 +12,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "fmrx_pll_core.h"
+
 namespace fmrx {
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
@@ -47,7 +49,7 @@ __device__ __forceinline__ float fm_discriminate(float ci, float cq, float pi_, 
 __device__ __forceinline__ float nco_from_trig(float trig_arg, float scale, float adjust)
 {
     const float a = fadd(fmul(trig_arg, scale), adjust);
-    return d2f(cos((double)a));
+    return pllcore::cos_of_float(a);   // exact reduction for |a| <= 2^24, library cos beyond
 }
 
 // src/filter.cpp:180-183

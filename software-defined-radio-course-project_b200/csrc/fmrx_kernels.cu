@@ -225,49 +225,51 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 // ============================================================================
 // K3: PLL recurrence (src/filter.cpp:157-171)
 // ============================================================================
-// The recurrence is a dependent chain (2 FMUL -> atan2 -> 4 float ops -> 2
-// double ops -> sincos), so one capture cannot use more than one thread's worth
-// of issue; throughput comes from running many captures side by side.  One
-// warp per capture: all 32 lanes execute the same chain on broadcast data (no
-// divergence), the warp loads 32 pilot samples with one coalesced request and
-// hands them out with shuffles, and lane t keeps the trigArg of step t so the
-// warp writes 32 results with one coalesced store.  Only trigArg leaves the
-// chain; the NCO output cos(trigArg*scale+adjust) is evaluated in K4.
+// The recurrence is one dependent chain per capture, so its latency bounds the
+// throughput of the whole receive chain; fmrx_pll_core.h holds the low-latency
+// formulation of one step (exact Cody-Waite sincos for float arguments; atan2 from
+// the previous step's reduced argument plus the FMA residuals of the roundings).
+// One warp per capture: all 32 lanes execute the same chain on broadcast data (no
+// divergence); the warp loads 32 pilot samples with one coalesced request, every
+// lane computes the double reciprocal of ITS sample (off the chain, 32 at a time),
+// both are handed out with shuffles, and lane t keeps the trigArg of step t so the
+// warp writes 32 results with one coalesced store.  Only trigArg leaves the chain;
+// the NCO output cos(trigArg*scale+adjust) is evaluated in K4.
 
 __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
 {
+    using namespace pllcore;
     const int c = blockIdx.x;
     const int lane = threadIdx.x;
     const float *p = a.pilot + (size_t)c * a.pilot_stride;
     float *tr = a.trig + (size_t)c * a.if_stride + a.if_off;
     float *st = a.state + 8 * (size_t)c;
 
-    float integ = st[0], ph = st[1], fi = st[2], fq = st[3], toff = st[5];
-    const float kp = a.prm.kp, ki = a.prm.ki;
-    const double w = a.prm.w;
+    Consts k;
+    k.kp = a.prm.kp;
+    k.ki = a.prm.ki;
+    k.w = a.prm.w;
+    Chain ch;
+    ch.integ = st[0];
+    ch.ph = st[1];
+    ch.fi = st[2];
+    ch.fq = st[3];
+    ch.toff = st[5];
+    bool valid = chain_load(ch, k);
     const int n = a.n_if;
-    float ta = 0.0f;
 
-    float pv_next = (lane < n) ? p[lane] : 0.0f;
+    float pv_next = (lane < n) ? p[lane] : 1.0f;
     for (int base = 0; base < n; base += 32) {
         const float pv = pv_next;
+        const double inv = 1.0 / (double)pv;            // this lane's sample; IEEE divide
         const int nb = base + 32 + lane;
-        pv_next = (nb < n) ? p[nb] : 0.0f;
+        pv_next = (nb < n) ? p[nb] : 1.0f;
         const int cnt = min(32, n - base);
         float tv = 0.0f;
         for (int t = 0; t < cnt; t++) {
             const float x = __shfl_sync(0xffffffffu, pv, t);
-            const float ei = fmul(x, fi);                               // :159
-            const float eq = fmul(x, -fq);                              // :160
-            const float ed = d2f(atan2((double)eq, (double)ei));        // :161
-            integ = fadd(integ, fmul(ki, ed));                          // :163
-            ph = fadd(ph, fadd(fmul(kp, ed), integ));                   // :164
-            toff = fadd(toff, 1.0f);                                    // :166 float counter
-            ta = d2f(dadd(dmul(w, (double)toff), (double)ph));          // :167
-            double sn, cs;
-            sincos((double)ta, &sn, &cs);
-            fi = d2f(cs);                                               // :168
-            fq = d2f(sn);                                               // :169
+            const double inv_x = __shfl_sync(0xffffffffu, inv, t);
+            const float ta = chain_step(ch, k, x, inv_x, valid, nullptr);
             if (lane == t)
                 tv = ta;
         }
@@ -275,13 +277,13 @@ __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
             tr[base + lane] = tv;
     }
     if (lane == 0) {
-        st[0] = integ;
-        st[1] = ph;
-        st[2] = fi;
-        st[3] = fq;
-        st[5] = toff;
+        st[0] = ch.integ;
+        st[1] = ch.ph;
+        st[2] = ch.fi;
+        st[3] = ch.fq;
+        st[5] = ch.toff;
         if (n > 0)
-            st[4] = nco_from_trig(ta, a.prm.scale, a.prm.adjust);      // :173
+            st[4] = nco_from_trig(ch.ta, a.prm.scale, a.prm.adjust);      // :173
     }
 }
 
@@ -327,11 +329,15 @@ __global__ void __launch_bounds__(kAudioTile) k_audio(const AudioArgs a, const i
     const int q_first = (n_lo >= kMonoDelay) ? ((n_lo - kMonoDelay) * D) / U
                                              : ((NA - kMonoDelay) * D) / U - B;
     const int r_min = q_first - (T - 1);
-    const int r_max = ((n_lo + kAudioTile - 1) * D) / U;
+    // the last tile of a block also stages the block's final samples (no audio frame of
+    // this block uses them, but the stage taps cover the whole block)
+    const int r_max = (n_lo + kAudioTile >= NA) ? B - 1 : ((n_lo + kAudioTile - 1) * D) / U;
+    // IF samples this tile "owns" for the optional nco/mixer stage taps: those past the
+    // previous tile's last staged sample
+    const int own_lo = n_lo ? ((n_lo - 1) * D) / U + 1 : 0;
+    const int own_hi = r_max + 1;
+    const int q_lo = (n_lo * D) / U;          // newest sample of the tile's first frame
     const int count = r_max - r_min + 1;
-    // IF samples this tile "owns" for the optional nco/mixer stage taps
-    const int own_lo = (n_lo * D) / U;
-    const int own_hi = (n_lo + kAudioTile >= NA) ? B : ((n_lo + kAudioTile) * D) / U;
 
     for (int i = tid; i < count; i += kAudioTile) {
         const int r = r_min + i;
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(kAudioTile) k_audio(const AudioArgs a, const i
             a.mixer[sg] = mx;
         }
     }
-    const bool need_tail = (own_lo - (T - 1)) < 0;
+    const bool need_tail = (q_lo - (T - 1)) < 0;
     if (need_tail)
         for (int i = tid; i < T - 1; i += kAudioTile)
             s_tail[i] = demod[blk0 + B - (T - 1) + i];
@@ -415,7 +421,7 @@ __global__ void __launch_bounds__(kAudioTile) k_audio(const AudioArgs a, const i
 
 static inline int audio_span(int T, int U, int D)
 {
-    return (int)(((long long)(kAudioTile + kMonoDelay - 1) * D + U - 1) / U) + T + 2;
+    return (int)(((long long)(kAudioTile + kMonoDelay) * D + U - 1) / U) + T + 2;
 }
 
 int audio_smem_bytes(int T, int U, int D)
