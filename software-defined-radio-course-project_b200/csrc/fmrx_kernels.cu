@@ -227,18 +227,34 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 // ============================================================================
 // The recurrence is one dependent chain per capture, so its latency bounds the
 // throughput of the whole receive chain; fmrx_pll_core.h holds the low-latency
-// formulation of one step (exact Cody-Waite sincos for float arguments; atan2 from
-// the previous step's reduced argument plus the FMA residuals of the roundings).
-// One warp per capture: all 32 lanes execute the same chain on broadcast data (no
-// divergence); the warp loads 32 pilot samples with one coalesced request, every
-// lane computes the double reciprocal of ITS sample (off the chain, 32 at a time),
-// both are handed out with shuffles, and lane t keeps the trigArg of step t so the
-// warp writes 32 results with one coalesced store.  Only trigArg leaves the chain;
-// the NCO output cos(trigArg*scale+adjust) is evaluated in K4.
+// formulation of one step and the measurements behind it.  One warp per capture:
+// all 32 lanes execute the same chain (no divergence).  Everything that does not
+// depend on the recurrence is produced 32 samples at a time, one lane per sample --
+// the coalesced pilot load, (double)x, the IEEE reciprocal 1/x, the half-turn flag
+// and w*trigOffset -- and parked in shared memory, from where each step fetches its
+// inputs with two broadcast LDS.128 issued one step ahead.  Steps run speculatively
+// in groups of 32 from a register checkpoint: guards only accumulate into a flag,
+// and a group with a failed guard (about one in 2000) is redone step by step with
+// the checked/generic step.  trigArg of each step is parked in shared memory by lane
+// 0 and written out coalesced per group.  Only trigArg leaves the chain; the NCO
+// output cos(trigArg*scale+adjust) is evaluated in K4.
+
+struct __align__(16) PllSlot {
+    float x;
+    int turn_hi;     // high word of 2.0 (x < 0) or 0.0
+    double xd;
+    double inv_x;
+    double v;
+};
+
+__device__ __forceinline__ void pin(double &v) { asm volatile("" : "+d"(v)); }
 
 __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
 {
     using namespace pllcore;
+    __shared__ PllSlot s_in[2][32];
+    __shared__ double s_ta[32];
+
     const int c = blockIdx.x;
     const int lane = threadIdx.x;
     const float *p = a.pilot + (size_t)c * a.pilot_stride;
@@ -249,41 +265,94 @@ __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
     k.kp = a.prm.kp;
     k.ki = a.prm.ki;
     k.w = a.prm.w;
+    TrigK K = trig_constants();
+    // keep the 18 constants in registers for the whole loop
+    pin(K.two_over_pi); pin(K.p1); pin(K.p2); pin(K.p3);
+    pin(K.s1); pin(K.s2); pin(K.s3); pin(K.s4); pin(K.s5); pin(K.s6);
+    pin(K.c1); pin(K.c2); pin(K.c3); pin(K.c4); pin(K.c5); pin(K.c6);
+    pin(K.pio2_hi); pin(K.pio2_lo);
+
     Chain ch;
     ch.integ = st[0];
     ch.ph = st[1];
     ch.fi = st[2];
     ch.fq = st[3];
     ch.toff = st[5];
-    bool valid = chain_load(ch, k);
+    chain_load(ch, k);
     const int n = a.n_if;
 
-    float pv_next = (lane < n) ? p[lane] : 1.0f;
-    for (int base = 0; base < n; base += 32) {
-        const float pv = pv_next;
-        const double inv = 1.0 / (double)pv;            // this lane's sample; IEEE divide
-        const int nb = base + 32 + lane;
-        pv_next = (nb < n) ? p[nb] : 1.0f;
+    // trigOffset after j steps is min(t0 + j, 2^24) when it starts integer-valued
+    const bool regular = toff_is_regular(ch.toff);
+    const int t0 = regular ? (int)ch.toff : 0;
+
+    auto prepare = [&](int base, int buf, float pvv) {
+        PllSlot sl;
+        sl.x = pvv;
+        sl.turn_hi = (pvv < 0.0f) ? 0x40000000 : 0;
+        sl.xd = (double)pvv;
+        sl.inv_x = 1.0 / sl.xd;                                  // IEEE divide
+        const float toff = (float)min(t0 + base + lane + 1, 16777216);   // exact: <= 2^24
+        sl.v = __dmul_rn(k.w, (double)toff);                     // :167 w*trigOffset
+        s_in[buf][lane] = sl;
+    };
+
+    float pv = (lane < n) ? p[lane] : 1.0f;
+    float pvn = (32 + lane < n) ? p[32 + lane] : 1.0f;
+    prepare(0, 0, pv);
+    __syncwarp();
+
+    for (int base = 0, g = 0; base < n; base += 32, g++) {
+        const int buf = g & 1;
+        const int nn = base + 64 + lane;
+        const float pvnn = (nn < n) ? p[nn] : 1.0f;
+        prepare(base + 32, buf ^ 1, pvn);
         const int cnt = min(32, n - base);
-        float tv = 0.0f;
-        for (int t = 0; t < cnt; t++) {
-            const float x = __shfl_sync(0xffffffffu, pv, t);
-            const double inv_x = __shfl_sync(0xffffffffu, inv, t);
-            const float ta = chain_step(ch, k, x, inv_x, valid, nullptr);
-            if (lane == t)
-                tv = ta;
+        const Chain ck = ch;
+        bool good = regular;
+        if (good) {
+            const float4 *slots = reinterpret_cast<const float4 *>(&s_in[buf][0]);
+            float4 q0 = slots[0], q1 = slots[1];
+            for (int t = 0; t < cnt; t++) {
+                const int tn = (t + 1) & 31;
+                const float4 n0 = slots[2 * tn], n1 = slots[2 * tn + 1];   // next step's inputs
+                StepIn in;
+                in.x = q0.x;
+                in.turn = __hiloint2double(__float_as_int(q0.y), 0);
+                in.xd = __hiloint2double(__float_as_int(q0.w), __float_as_int(q0.z));
+                in.inv_x = __hiloint2double(__float_as_int(q1.y), __float_as_int(q1.x));
+                in.v = __hiloint2double(__float_as_int(q1.w), __float_as_int(q1.z));
+                good &= chain_step_spec(ch, k, K, in);
+                if (lane == 0)
+                    s_ta[t] = ch.tad;
+                q0 = n0;
+                q1 = n1;
+            }
         }
+        if (!good) {
+            ch = ck;
+            for (int t = 0; t < cnt; t++) {
+                const float ta = chain_step(ch, k, K, s_in[buf][t].x, nullptr);
+                if (lane == 0)
+                    s_ta[t] = (double)ta;
+            }
+        }
+        __syncwarp();
         if (lane < cnt)
-            tr[base + lane] = tv;
+            tr[base + lane] = __double2float_rn(s_ta[lane]);
+        __syncwarp();
+        pv = pvn;
+        pvn = pvnn;
     }
     if (lane == 0) {
+        float fi, fq;
+        chain_feedback(ch, fi, fq);
         st[0] = ch.integ;
         st[1] = ch.ph;
-        st[2] = ch.fi;
-        st[3] = ch.fq;
+        st[2] = fi;
+        st[3] = fq;
         st[5] = ch.toff;
         if (n > 0)
-            st[4] = nco_from_trig(ch.ta, a.prm.scale, a.prm.adjust);      // :173
+            st[4] = nco_from_trig(__double2float_rn(ch.tad), a.prm.scale, a.prm.adjust);   // :173
     }
 }
 

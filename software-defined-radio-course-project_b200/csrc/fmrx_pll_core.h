@@ -5,30 +5,41 @@
 //
 // Why a special formulation.  Per IF sample the reference evaluates, in double,
 // atan2(eQ,eI), cos(trigArg) and sin(trigArg) and rounds each to float.  The
-// recurrence is one dependent chain per capture, so its LATENCY is the throughput
-// bound of the whole receive chain.  Stock libdevice sin/cos fall into the
-// Payne-Hanek slow path once |trigArg| > 105615 (0.9 s into a capture), and stock
-// atan2 is a division plus a degree-19 polynomial.  Here:
+// recurrence is one dependent chain per capture, so its LATENCY (and, with one
+// warp per capture, its instruction count) is the throughput bound of the whole
+// receive chain.  Measured on B200 (tools/ubench_latency*.cu): DFMA/DADD/DMUL
+// 8.5 cycles, FP32 4.4, each f32<->f64 conversion 18, DSETP+select 12.  Stock
+// libdevice sin/cos fall into the Payne-Hanek slow path once |trigArg| > 105615
+// (0.9 s into a capture) and stock atan2 is a division plus a degree-19
+// polynomial: 760 cycles per sample.  Here (about 250):
 //
-//  * sincos: trigArg is a FLOAT (24-bit significand, |x| < 2^24) promoted to
+//  * sincos: trigArg is a FLOAT (24-bit significand, |x| <= 2^24) promoted to
 //    double, so a 3-term Cody-Waite reduction with 29/29/53-bit pieces of pi/2 is
 //    exact in its first two steps (n < 2^24: n*P1 and n*P2 are exact products) and
 //    rounds once; the kernels are the fdlibm minimax polynomials, Estrin-ordered.
-//  * atan2: its arguments are eI = fl(x*fI), eQ = fl(x*(-fQ)) with (fI,fQ) =
-//    fl(cos), fl(sin) of the PREVIOUS trigArg, whose reduced argument r and
-//    quadrant n are already known.  So atan2(eQ,eI) = -(phi + delta) where phi is
-//    the wrapped previous trigArg (r + quadrant constant, shifted by pi when x<0)
-//    and delta is the tiny rotation caused by the four float roundings, obtained
-//    exactly from the FMA residuals t_i = eI - x*cos, t_q = eQ + x*sin:
-//        cross = -(cos*t_q + sin*t_i)/x,  dot = (cos*t_i - sin*t_q)/x,
+//  * no quadrant rotation on the chain: the feedback pair is kept UNROTATED,
+//    (cf, sf) = fl32(cos r, sin r) of the reduced argument r.  The reference's
+//    fI, fQ are a signed permutation of that pair and float multiplication commutes
+//    with signed permutations, so eI, eQ are the same signed permutation of
+//    fl(x*cf), fl(x*(-sf)) and atan2 only needs the quadrant added back as an angle.
+//  * atan2(eQ,eI) = -(phi + delta): phi = r + j*pi/2 is the previous trigArg wrapped
+//    to (-pi, pi] (j = quadrant count mod 4 in -2..2, shifted by 2 when the pilot
+//    sample is negative), and delta is the tiny rotation caused by the float
+//    roundings, obtained exactly from FMA residuals t_i = eI - x*cos r,
+//    t_q = eQ + x*sin r:
+//        cross = -(cos r*t_q + sin r*t_i)/x,  dot = (cos r*t_i - sin r*t_q)/x,
 //        delta = cross*(1 - dot)            (|cross|,|dot| <~ 2^-23; O(2^-69) dropped)
-//    Anything unusual (x = 0, subnormal products, |phi| near pi, NaN) fails the
-//    guard and takes the reference formulation (true atan2) for that step.
+//  * trigArg = fl32(w*toff + ph) is rounded inside double by the add-magic trick
+//    for the binade trigArg currently lives in (2 DADD instead of 2 conversions).
+//  * every assumption (x normal, roundings tiny, phi clear of the +-pi seam, binade
+//    unchanged) is a guard evaluated OFF the dependent chain; a step whose guard
+//    fails commits nothing and is redone by the generic step (the reference's
+//    statements with the library atan2): ~25 of 2.4 million steps.
 //
-// Both evaluate the same real function the reference does, to ~1 ulp of double,
-// and round to float where the reference rounds; they differ from glibc's result
-// only when the exact value lies within ~1e-16 relative of a float rounding
-// boundary (~1e-8 per sample), the same class of event as using any other libm.
+// Both formulations evaluate the same real functions the reference does, to ~1 ulp
+// of double, and round to float where the reference rounds; they differ from
+// glibc's result only when the exact value lies within ~1e-16 relative of a float
+// rounding boundary (~1e-8 per sample), the same class of event as any other libm.
 #pragma once
 
 #include <math.h>
@@ -36,7 +47,7 @@
 #include <string.h>
 
 #if defined(__CUDACC__)
-#define FMRX_HD __host__ __device__ __forceinline__
+#define FMRX_HD __device__ __forceinline__
 #else
 #define FMRX_HD static inline
 #endif
@@ -44,14 +55,14 @@
 namespace pllcore {
 
 // ---- exact-rounding primitives ---------------------------------------------
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 FMRX_HD double p_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
 FMRX_HD double p_mul(double a, double b) { return __dmul_rn(a, b); }
 FMRX_HD double p_add(double a, double b) { return __dadd_rn(a, b); }
 FMRX_HD float p_fmulf(float a, float b) { return __fmul_rn(a, b); }
 FMRX_HD float p_faddf(float a, float b) { return __fadd_rn(a, b); }
 FMRX_HD float p_d2f(double a) { return __double2float_rn(a); }
-FMRX_HD int p_lo32(double a) { return __double2loint(a); }
+FMRX_HD int p_hi32(double a) { return __double2hiint(a); }
 #else
 // host build: compiled with -ffp-contract=off, so * and + are single IEEE ops
 FMRX_HD double p_fma(double a, double b, double c) { return fma(a, b, c); }
@@ -60,180 +71,310 @@ FMRX_HD double p_add(double a, double b) { return a + b; }
 FMRX_HD float p_fmulf(float a, float b) { return a * b; }
 FMRX_HD float p_faddf(float a, float b) { return a + b; }
 FMRX_HD float p_d2f(double a) { return (float)a; }
-FMRX_HD int p_lo32(double a)
+FMRX_HD int p_hi32(double a)
 {
     uint64_t u;
     memcpy(&u, &a, sizeof(u));
-    return (int)(uint32_t)u;
+    return (int)(uint32_t)(u >> 32);
 }
 #endif
 
 // ---- constants ---------------------------------------------------------------
-// pi/2 = P1 + P2 + P3: 29 + 29 + 53 bits (n*P1, n*P2 exact for |n| < 2^24, which
-// covers every float argument |x| <= 2^24)
-#define FMRX_PIO2_1 1.570796325802803       /* 0x1.921fb54000000p+0  */
-#define FMRX_PIO2_2 9.920935774287987e-10   /* 0x1.10b4611000000p-30 */
-#define FMRX_PIO2_3 2.2517417741562176e-18  /* 0x1.4c4c6628b80dcp-59 */
-#define FMRX_FAST_TRIG_MAX 16777216.0f      /* |x| <= 2^24 */
-#define FMRX_2_OVER_PI 0.6366197723675814  /* 0x1.45f306dc9c883p-1  */
+#define FMRX_FAST_TRIG_MAX 16777216.0f     /* |x| <= 2^24 */
 #define FMRX_RINT_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
-#define FMRX_PIO2_HI 1.5707963267948966
-#define FMRX_PIO2_LO 6.123233995736766e-17
-#define FMRX_PI_HI 3.141592653589793
-#define FMRX_PI_LO 1.2246467991473532e-16
 
-// What one sincos leaves behind for the next step's atan2 shortcut.
-struct Trig {
-    double cs, sn;   // cos, sin of the float argument, in double (~1 ulp)
-    double r;        // reduced argument in [-pi/4, pi/4]
-    int n;           // quadrant count: argument = r + n*pi/2
+// pi/2 = P1 + P2 + P3: 29 + 29 + 53 bits (n*P1, n*P2 exact for |n| < 2^24, which
+// covers every float argument |x| <= 2^24).  The constants travel as a struct so the
+// device loop can pin them in registers once (k_pll) instead of re-loading 64-bit
+// immediates / constant-bank words every step.
+struct TrigK {
+    double two_over_pi;          // 0x1.45f306dc9c883p-1
+    double p1, p2, p3;           // 0x1.921fb54000000p+0, 0x1.10b4611000000p-30, 0x1.4c4c6628b80dcp-59
+    double s1, s2, s3, s4, s5, s6;   // fdlibm __kernel_sin
+    double c1, c2, c3, c4, c5, c6;   // fdlibm __kernel_cos
+    double pio2_hi, pio2_lo;
 };
-
-// sin and cos of a float-valued argument |x| <= 2^24 (x = (double)float).
-FMRX_HD Trig sincos_f32arg(double x)
+#define FMRX_TRIGK_INIT                                                                  \
+    {                                                                                    \
+        0.6366197723675814, 1.570796325802803, 9.920935774287987e-10,                    \
+            2.2517417741562176e-18, -1.66666666666666324348e-01,                         \
+            8.33333333332248946124e-03, -1.98412698298579493134e-04,                     \
+            2.75573137070700676789e-06, -2.50507602534068634195e-08,                     \
+            1.58969099521155010221e-10, 4.16666666666666019037e-02,                      \
+            -1.38888888888741095749e-03, 2.48015872894767294178e-05,                     \
+            -2.75573143513906633035e-07, 2.08757232129817482790e-09,                     \
+            -1.13596475577881948265e-11, 1.5707963267948966, 6.123233995736766e-17       \
+    }
+FMRX_HD TrigK trig_constants()
 {
-    // n = rint(x * 2/pi) by the add-magic trick; low word of the sum is n
-    const double qm = p_add(p_mul(x, FMRX_2_OVER_PI), FMRX_RINT_MAGIC);
+    const TrigK k = FMRX_TRIGK_INIT;
+    return k;
+}
+
+// sin r, cos r of the reduced argument and the quadrant count nd (an integer held
+// in a double) of a float-valued argument |x| <= 2^24: x = r + nd*pi/2.
+FMRX_HD void sincos_reduced(const TrigK &K, double x, double &sn_r, double &cs_r, double &r_out,
+                            double &nd_out)
+{
+    // nd = rint(x * 2/pi) by the add-magic trick (fused: one rounding).  A
+    // tie-adjacent miss only moves |r| a hair past pi/4.
+    const double qm = p_fma(x, K.two_over_pi, FMRX_RINT_MAGIC);
     const double nd = p_add(qm, -FMRX_RINT_MAGIC);
-    double r = p_fma(-nd, FMRX_PIO2_1, x);      // exact
-    r = p_fma(-nd, FMRX_PIO2_2, r);             // exact product, one rounding
-    r = p_fma(-nd, FMRX_PIO2_3, r);
+    double r = p_fma(-nd, K.p1, x);         // exact
+    r = p_fma(-nd, K.p2, r);                // exact product, one rounding
+    r = p_fma(-nd, K.p3, r);
     const double z = p_mul(r, r);
     const double z2 = p_mul(z, z);
     const double z4 = p_mul(z2, z2);
-    // fdlibm __kernel_sin: sin r = r + r*z*(S1 + z*S2 + ... + z^5*S6)
-    const double s12 = p_fma(8.33333333332248946124e-03, z, -1.66666666666666324348e-01);
-    const double s34 = p_fma(2.75573137070700676789e-06, z, -1.98412698298579493134e-04);
-    const double s56 = p_fma(1.58969099521155010221e-10, z, -2.50507602534068634195e-08);
+    // sin r = r + r*z*(S1 + z*S2 + ... + z^5*S6), Estrin order
+    const double s12 = p_fma(K.s2, z, K.s1);
+    const double s34 = p_fma(K.s4, z, K.s3);
+    const double s56 = p_fma(K.s6, z, K.s5);
     double ps = p_fma(s34, z2, s12);
     ps = p_fma(s56, z4, ps);
-    const double sn = p_fma(p_mul(z, r), ps, r);
-    // fdlibm __kernel_cos: cos r = 1 - z/2 + z^2*(C1 + z*C2 + ... + z^5*C6)
-    const double c12 = p_fma(-1.38888888888741095749e-03, z, 4.16666666666666019037e-02);
-    const double c34 = p_fma(-2.75573143513906633035e-07, z, 2.48015872894767294178e-05);
-    const double c56 = p_fma(-1.13596475577881948265e-11, z, 2.08757232129817482790e-09);
+    sn_r = p_fma(p_mul(z, r), ps, r);
+    // cos r = 1 - z/2 + z^2*(C1 + z*C2 + ... + z^5*C6)
+    const double c12 = p_fma(K.c2, z, K.c1);
+    const double c34 = p_fma(K.c4, z, K.c3);
+    const double c56 = p_fma(K.c6, z, K.c5);
     double pc = p_fma(c34, z2, c12);
     pc = p_fma(c56, z4, pc);
-    const double cs = p_fma(z2, pc, p_fma(-0.5, z, 1.0));
+    cs_r = p_fma(z2, pc, p_fma(-0.5, z, 1.0));
+    r_out = r;
+    nd_out = nd;
+}
 
-    Trig t;
-    t.r = r;
-    t.n = p_lo32(qm);
-    // rotate by n quadrants
-    const int q = t.n & 3;
-    const double a = (q & 1) ? cs : sn;          // |sin|
-    const double b = (q & 1) ? sn : cs;          // |cos|
-    t.sn = (q & 2) ? -a : a;
-    t.cs = ((q + 1) & 2) ? -b : b;
-    return t;
+// Rotate (sin r, cos r) by n quadrants (used off the chain only).
+template <class T> FMRX_HD void rotate_quadrant(int n, T sn_r, T cs_r, T &sn, T &cs)
+{
+    const int q = n & 3;
+    const T a = (q & 1) ? cs_r : sn_r;
+    const T b = (q & 1) ? sn_r : cs_r;
+    sn = (q & 2) ? -a : a;
+    cs = ((q + 1) & 2) ? -b : b;
 }
 
 // cos of a float, rounded to float, for the NCO output (src/filter.cpp:170): same
 // reduction; arguments beyond its range take the library cos.
 FMRX_HD float cos_of_float(float a)
 {
-    if (fabsf(a) <= FMRX_FAST_TRIG_MAX)
-        return p_d2f(sincos_f32arg((double)a).cs);
+    if (fabsf(a) <= FMRX_FAST_TRIG_MAX) {
+        double sn_r, cs_r, r, nd, sn, cs;
+        const TrigK K = trig_constants();
+        sincos_reduced(K, (double)a, sn_r, cs_r, r, nd);
+        rotate_quadrant((int)nd, sn_r, cs_r, sn, cs);
+        return p_d2f(cs);
+    }
     return p_d2f(cos((double)a));
 }
 
-// PLL state carried between steps (superset of the reference's five floats: the
-// double-precision leftovers of the last sincos feed the atan2 shortcut; they are
-// a pure function of (trigOffset, phaseEst), so they are recomputed, not stored,
-// when a state is loaded).
-struct Chain {
-    float integ, ph, fi, fq, toff;
-    Trig trig;       // of the last trigArg (what fi, fq were rounded from)
-    float ta;        // last trigArg
-};
+// r + j*pi/2 for the quadrant count m (an integer in a double), with
+// j = m - 4*rint(m/4) in -2..2: the argument wrapped to (-pi, pi].  For m = 2
+// (mod 4) the tie goes to even, so the result may land just outside that interval;
+// this only happens next to the +-pi seam, where the guard sends the step to the
+// generic path anyway.
+FMRX_HD double wrapped_angle(const TrigK &K, double m, double r)
+{
+    const double t = p_add(p_fma(m, 0.25, FMRX_RINT_MAGIC), -FMRX_RINT_MAGIC);
+    const double jd = p_fma(-4.0, t, m);        // exact
+    return p_fma(jd, K.pio2_hi, p_fma(jd, K.pio2_lo, r));
+}
 
 struct Consts {
     float kp, ki;
     double w;        // (2*PI)*(double)(freq/Fs)
 };
 
-// Rebuild the derived fields after loading (integ, ph, fi, fq, toff).  The
-// reference's initial state is fi=1, fq=0 with no trigArg behind it; that pair is
-// cos/sin of 0, and any state saved by this code satisfies fi,fq = fl(cos,sin)(ta)
-// with ta = fl(w*toff + ph).  `consistent` tells the step whether the shortcut
-// may trust trig for the next sample.
-FMRX_HD bool chain_load(Chain &c, const Consts &k)
-{
-    const float ta = p_d2f(p_add(p_mul(k.w, (double)c.toff), (double)c.ph));
-    c.ta = ta;
-    if (!(fabsf(ta) <= FMRX_FAST_TRIG_MAX))
-        return false;
-    c.trig = sincos_f32arg((double)ta);
-    return p_d2f(c.trig.cs) == c.fi && p_d2f(c.trig.sn) == c.fq;
-}
+// PLL state carried between steps: the reference's floats plus the double
+// leftovers of the last sincos (a pure function of trigOffset and phaseEst: they
+// are recomputed, never stored, when a state is loaded).
+struct Chain {
+    float integ, ph, toff;
+    double tad;          // last trigArg (a float value, held in a double)
+    float fi, fq;        // the reference's feedbackI/Q; maintained by the generic
+                         // step only -- read them through chain_feedback()
+    float cf, sf;        // fl32(cos r), fl32(sin r): the unrotated feedback pair
+    double cr, sr;       // cos r, sin r
+    double r, nd;        // ta = r + nd*pi/2
+    // trigArg = fl32(w*toff + ph) is rounded in double as (s + magic) - magic, which
+    // is the float rounding while |s| stays in the binade whose exponent field is
+    // `binade` (high word of 2^e).  FMRX_DISARMED switches the fast step off: the
+    // generic step runs and re-arms it.
+    double magic;
+    unsigned binade;
+};
 
-// atan2(eq, ei) for ei = fl(x*fi), eq = fl(x*(-fq)); returns false if the guard
-// rejects the shortcut (caller then evaluates the true atan2).
-FMRX_HD bool atan2_shortcut(const Trig &t, float x, double inv_x, float ei, float eq, double *out)
+#define FMRX_DISARMED 0x80000000u
+
+FMRX_HD void chain_arm(Chain &c)
 {
-    const double xd = (double)x;
-    const double ti = p_fma(-xd, t.cs, (double)ei);   // = x*du (exact residual, rounded once)
-    const double tq = p_fma(xd, t.sn, (double)eq);    // = -x*dv
-    const double cross = -p_mul(p_fma(t.sn, ti, p_mul(t.cs, tq)), inv_x);
-    const double dotc = p_mul(p_fma(-t.sn, tq, p_mul(t.cs, ti)), inv_x);
-    const double delta = p_fma(-cross, dotc, cross);
-    // phi: the wrapped angle of (cos, sin), turned by pi when x < 0
-    const int kk = (t.n + (x < 0.0f ? 2 : 0)) & 3;
-    double chi, clo;
-    if (kk == 0) {
-        chi = 0.0; clo = 0.0;
-    } else if (kk == 1) {
-        chi = FMRX_PIO2_HI; clo = FMRX_PIO2_LO;
-    } else if (kk == 3) {
-        chi = -FMRX_PIO2_HI; clo = -FMRX_PIO2_LO;
-    } else if (t.r > 0.0) {
-        chi = -FMRX_PI_HI; clo = -FMRX_PI_LO;
+    const float at = fabsf(p_d2f(c.tad));
+    if (at >= 0x1p-60f && at < FMRX_FAST_TRIG_MAX) {
+        int e;
+        (void)frexpf(at, &e);                 // at = m * 2^e, m in [0.5, 1)
+        c.binade = (unsigned)(e - 1 + 1023) << 20;
+        c.magic = ldexp(1.5, e - 1 + 29);
     } else {
-        chi = FMRX_PI_HI; clo = FMRX_PI_LO;
+        c.binade = FMRX_DISARMED;
+        c.magic = 0.0;
     }
-    const double phi = p_add(p_add(t.r, clo), chi);
-    const double alpha = p_add(phi, delta);
-    *out = -alpha;
-    // guard: roundings must be tiny rotations, and stay clear of the +-pi seam
-    return fabs(cross) < 0x1p-20 && fabs(dotc) < 0x1p-20 && fabs(phi) < 3.125;
 }
 
-#if defined(__CUDA_ARCH__)
-FMRX_HD double ref_atan2(double y, double x) { return atan2(y, x); }
-#else
-FMRX_HD double ref_atan2(double y, double x) { return atan2(y, x); }
-#endif
-
-// One step.  x = pilot sample, inv_x = 1.0/(double)x (computed off the chain).
-// trig_valid (in/out): c.trig describes the trigArg that fi, fq were rounded from.
-// Returns the float trigArg of this step; *slow counts guard rejections.
-FMRX_HD float chain_step(Chain &c, const Consts &k, float x, double inv_x, bool &trig_valid,
-                         unsigned *slow)
+// The reference's feedbackI, feedbackQ of the current state.
+FMRX_HD void chain_feedback(const Chain &c, float &fi, float &fq)
 {
-    const float ei = p_fmulf(x, c.fi);                               // :159
-    const float eq = p_fmulf(x, -c.fq);                              // :160
-    double ang;
-    if (!(trig_valid && atan2_shortcut(c.trig, x, inv_x, ei, eq, &ang))) {
-        ang = ref_atan2((double)eq, (double)ei);                     // :161
-        if (slow)
-            ++*slow;
+    if (c.binade != FMRX_DISARMED) {
+        rotate_quadrant((int)c.nd, c.sf, c.cf, fq, fi);
+    } else {
+        fi = c.fi;
+        fq = c.fq;
     }
-    const float ed = p_d2f(ang);
+}
+
+// Recompute the sincos leftovers for c.ta (|ta| <= 2^24) and arm the fast step.
+FMRX_HD void chain_refresh(Chain &c)
+{
+    const TrigK K = trig_constants();
+    sincos_reduced(K, c.tad, c.sr, c.cr, c.r, c.nd);
+    c.sf = p_d2f(c.sr);
+    c.cf = p_d2f(c.cr);
+    rotate_quadrant((int)c.nd, c.sf, c.cf, c.fq, c.fi);              // :168-169
+    chain_arm(c);
+}
+
+// Load (integ, ph, fi, fq, toff) and rebuild the derived fields.  A state written
+// by this code (or the reference's initial state fi=1, fq=0, toff=ph=0) satisfies
+// fi, fq = fl32(cos, sin)(fl32(w*toff + ph)); anything else disarms the fast step
+// for one sample.
+FMRX_HD void chain_load(Chain &c, const Consts &k)
+{
+    const float fi = c.fi, fq = c.fq;
+    const float ta = p_d2f(p_add(p_mul(k.w, (double)c.toff), (double)c.ph));
+    c.tad = (double)ta;
+    c.cr = c.sr = c.r = c.nd = c.magic = 0.0;
+    c.cf = c.sf = 0.0f;
+    c.binade = FMRX_DISARMED;
+    if (!(fabsf(ta) <= FMRX_FAST_TRIG_MAX))
+        return;
+    chain_refresh(c);
+    if (!(c.fi == fi && c.fq == fq)) {
+        c.fi = fi;
+        c.fq = fq;
+        c.binade = FMRX_DISARMED;
+    }
+}
+
+// The generic step: the reference's statements one by one (library atan2).
+FMRX_HD void chain_step_generic(Chain &c, const Consts &k, float x)
+{
+    float fi, fq;
+    chain_feedback(c, fi, fq);
+    const float ei = p_fmulf(x, fi);                                 // :159
+    const float eq = p_fmulf(x, -fq);                                // :160
+    const float ed = p_d2f(atan2((double)eq, (double)ei));           // :161
     c.integ = p_faddf(c.integ, p_fmulf(k.ki, ed));                   // :163
     c.ph = p_faddf(c.ph, p_faddf(p_fmulf(k.kp, ed), c.integ));       // :164
     c.toff = p_faddf(c.toff, 1.0f);                                  // :166
-    c.ta = p_d2f(p_add(p_mul(k.w, (double)c.toff), (double)c.ph));   // :167
-    if (fabsf(c.ta) <= FMRX_FAST_TRIG_MAX) {
-        c.trig = sincos_f32arg((double)c.ta);
-        c.fi = p_d2f(c.trig.cs);                                     // :168
-        c.fq = p_d2f(c.trig.sn);                                     // :169
-        trig_valid = true;
+    const float ta = p_d2f(p_add(p_mul(k.w, (double)c.toff), (double)c.ph));   // :167
+    c.tad = (double)ta;
+    if (fabsf(ta) <= FMRX_FAST_TRIG_MAX) {
+        chain_refresh(c);
     } else {   // beyond the exact-reduction range (or NaN): library sin/cos
-        c.fi = p_d2f(cos((double)c.ta));
-        c.fq = p_d2f(sin((double)c.ta));
-        trig_valid = false;
+        c.fi = p_d2f(cos(c.tad));                                    // :168
+        c.fq = p_d2f(sin(c.tad));                                    // :169
+        c.binade = FMRX_DISARMED;
     }
-    return c.ta;
+}
+
+// Per-sample inputs that do not depend on the recurrence: prepared off the chain
+// (on the device: one lane per sample, 32 at a time).
+struct StepIn {
+    float x;         // pilot sample
+    double xd;       // (double)x
+    double inv_x;    // 1.0 / (double)x, IEEE divide
+    double turn;     // 2.0 if x < 0 else 0.0: half a turn, in quadrants
+    double v;        // w * (double)trigOffset_after_this_step (:166-167)
+};
+
+FMRX_HD StepIn step_inputs(const Consts &k, float x, float toff_after)
+{
+    StepIn in;
+    in.x = x;
+    in.xd = (double)x;
+    in.inv_x = 1.0 / in.xd;
+    in.turn = (x < 0.0f) ? 2.0 : 0.0;
+    in.v = p_mul(k.w, (double)toff_after);
+    return in;
+}
+
+// The speculative fast step: ALWAYS updates the state, through the low-latency
+// formulation, and returns whether every guard held.  When it returns false the
+// state is garbage and the caller must restore a checkpoint (k_pll checkpoints
+// once per 32 steps and redoes the group step by step).  No guard sits on the
+// dependent chain.
+FMRX_HD bool chain_step_spec(Chain &c, const Consts &k, const TrigK &K, const StepIn &in)
+{
+    // ---- atan2(eq, ei) = -(phi + delta), in the unrotated frame --------------------
+    const double phi = wrapped_angle(K, p_add(c.nd, in.turn), c.r);
+    const double csx = p_mul(c.cr, in.inv_x);
+    const double snx = p_mul(c.sr, in.inv_x);
+    const float ei = p_fmulf(in.x, c.cf);                            // :159 (up to the quadrant)
+    const float eq = p_fmulf(in.x, -c.sf);                           // :160
+    const double ti = p_fma(-in.xd, c.cr, (double)ei);   // exact rounding residuals, rounded once
+    const double tq = p_fma(in.xd, c.sr, (double)eq);
+    const double m1 = p_mul(csx, tq);
+    const double cross = -p_fma(snx, ti, m1);                  // rotation by the roundings
+    const double dotc = p_fma(-snx, tq, p_mul(csx, ti));       // radial part (second order)
+    const double a1 = p_fma(-snx, ti, p_add(phi, -m1));        // phi + cross
+    const double alpha = p_fma(-cross, dotc, a1);              // phi + cross*(1 - dotc)
+    const float ed = p_d2f(-alpha);                                  // :161
+    bool ok = fabs(cross) < 0x1p-20 && fabs(dotc) < 0x1p-20 && fabs(phi) < 3.125;
+
+    // ---- loop filter (float, the reference's order) --------------------------------
+    c.integ = p_faddf(c.integ, p_fmulf(k.ki, ed));                   // :163
+    c.ph = p_faddf(c.ph, p_faddf(p_fmulf(k.kp, ed), c.integ));       // :164
+    c.toff = p_faddf(c.toff, 1.0f);                                  // :166
+    const double s = p_add(in.v, (double)c.ph);                      // :167 in double ...
+    ok = ok && (((unsigned)p_hi32(s) & 0x7fffffffu) - c.binade) < 0x00100000u;
+    c.tad = p_add(p_add(s, c.magic), -c.magic);                      // ... stored to float
+
+    // ---- sin, cos of the new trigArg -----------------------------------------------
+    sincos_reduced(K, c.tad, c.sr, c.cr, c.r, c.nd);
+    c.sf = p_d2f(c.sr);                                              // :168-169 (up to the quadrant)
+    c.cf = p_d2f(c.cr);
+    return ok;
+}
+
+// The checked fast step: commits only if every guard held.
+FMRX_HD bool chain_step_fast(Chain &c, const Consts &k, const TrigK &K, const StepIn &in)
+{
+    Chain t = c;
+    if (!chain_step_spec(t, k, K, in))
+        return false;
+    c = t;
+    return true;
+}
+
+// One checked step; *slow counts steps that took the generic path.  Returns trigArg.
+FMRX_HD float chain_step(Chain &c, const Consts &k, const TrigK &K, float x, unsigned *slow)
+{
+    const StepIn in = step_inputs(k, x, p_faddf(c.toff, 1.0f));
+    if (!chain_step_fast(c, k, K, in)) {
+        chain_step_generic(c, k, x);
+        if (slow)
+            ++*slow;
+    }
+    return p_d2f(c.tad);
+}
+
+// trigOffset advances by float additions of 1 (:166).  From an integer-valued start
+// in [0, 2^24] the value after j steps is min(start + j, 2^24) exactly (2^24 + 1
+// rounds back to 2^24: the counter saturates), which lets the device prepare
+// StepIn::v for 32 steps at once.  Any other start takes the step-by-step path.
+FMRX_HD bool toff_is_regular(float t) { return t >= 0.0f && t <= 16777216.0f && t == floorf(t); }
+FMRX_HD float toff_after(float start, int steps)
+{
+    return fminf(start + (float)steps, 16777216.0f);
 }
 
 }  // namespace pllcore

@@ -4,6 +4,7 @@
 // product library never contains a host PLL.
 // Build: g++ -O2 -ffp-contract=off [-mfma] -shared -fPIC (tests/conftest.py).
 #include <cstddef>
+#include <cstring>
 #include "fmrx_pll_core.h"
 
 using namespace pllcore;
@@ -19,17 +20,36 @@ int pll_model_run(const float *pilot, int n, float freq, float Fs, float bw, flo
     k.ki = (bw * bw) * 3.555f;
     k.w = (2.0 * 3.14159265358979323846) * (double)(freq / Fs);
     Chain c;
+    memset(&c, 0, sizeof(c));
     c.integ = state5[0]; c.ph = state5[1]; c.fi = state5[2]; c.fq = state5[3]; c.toff = state5[4];
-    bool valid = chain_load(c, k);
+    chain_load(c, k);
+    const TrigK K = trig_constants();
     unsigned slow = 0;
-    for (int i = 0; i < n; i++) {
-        const float x = pilot[i];
-        const double inv_x = 1.0 / (double)x;
-        const float ta = chain_step(c, k, x, inv_x, valid, &slow);
-        if (trig_out)
-            trig_out[i] = ta;
+    // mirrors k_pll: groups of 32 steps run speculatively from a checkpoint; a group
+    // with a failed guard is redone step by step
+    for (int base = 0; base < n; base += 32) {
+        const int cnt = n - base < 32 ? n - base : 32;
+        const Chain ck = c;
+        bool good = toff_is_regular(c.toff);
+        if (good) {
+            for (int t = 0; t < cnt; t++) {
+                const StepIn in = step_inputs(k, pilot[base + t], toff_after(ck.toff, t + 1));
+                good &= chain_step_spec(c, k, K, in);
+                if (trig_out)
+                    trig_out[base + t] = (float)c.tad;
+            }
+        }
+        if (!good) {
+            c = ck;
+            for (int t = 0; t < cnt; t++) {
+                const float ta = chain_step(c, k, K, pilot[base + t], &slow);
+                if (trig_out)
+                    trig_out[base + t] = ta;
+            }
+        }
     }
-    state5[0] = c.integ; state5[1] = c.ph; state5[2] = c.fi; state5[3] = c.fq; state5[4] = c.toff;
+    state5[0] = c.integ; state5[1] = c.ph; state5[4] = c.toff;
+    chain_feedback(c, state5[2], state5[3]);
     if (slow_steps)
         *slow_steps = slow;
     return 0;
@@ -39,8 +59,10 @@ int pll_model_run(const float *pilot, int n, float freq, float Fs, float bw, flo
 void pll_model_sincos(const float *x, int n, float *s, float *c)
 {
     for (int i = 0; i < n; i++) {
-        const Trig t = sincos_f32arg((double)x[i]);
-        s[i] = (float)t.sn;
+        double sr, cr, r, nd, sn, cs;
+        sincos_reduced(trig_constants(), (double)x[i], sr, cr, r, nd);
+        rotate_quadrant((int)nd, sr, cr, sn, cs);
+        s[i] = (float)sn;
         c[i] = cos_of_float(x[i]);
     }
 }
@@ -48,9 +70,9 @@ void pll_model_sincos(const float *x, int n, float *s, float *c)
 void pll_model_sincos_d(const float *x, int n, double *s, double *c)
 {
     for (int i = 0; i < n; i++) {
-        const Trig t = sincos_f32arg((double)x[i]);
-        s[i] = t.sn;
-        c[i] = t.cs;
+        double sr, cr, r, nd;
+        sincos_reduced(trig_constants(), (double)x[i], sr, cr, r, nd);
+        rotate_quadrant((int)nd, sr, cr, s[i], c[i]);
     }
 }
 
