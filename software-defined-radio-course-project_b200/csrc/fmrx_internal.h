@@ -57,6 +57,7 @@ struct PllArgs {
     int n_if;
     float *state;           // capture c at state + 8*c: integ, phase, fbI, fbQ, ncoLast, trigOffset
     PllParams prm;
+    pllcore::TrigK kconst;  // filled by launch_pll: read as constant-bank operands in the loop
 };
 cudaError_t launch_pll(const PllArgs &a, int n_captures, cudaStream_t s);
 

@@ -247,8 +247,6 @@ struct __align__(16) PllSlot {
     double v;
 };
 
-__device__ __forceinline__ void pin(double &v) { asm volatile("" : "+d"(v)); }
-
 __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
 {
     using namespace pllcore;
@@ -265,12 +263,7 @@ __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
     k.kp = a.prm.kp;
     k.ki = a.prm.ki;
     k.w = a.prm.w;
-    TrigK K = trig_constants();
-    // keep the 18 constants in registers for the whole loop
-    pin(K.two_over_pi); pin(K.p1); pin(K.p2); pin(K.p3);
-    pin(K.s1); pin(K.s2); pin(K.s3); pin(K.s4); pin(K.s5); pin(K.s6);
-    pin(K.c1); pin(K.c2); pin(K.c3); pin(K.c4); pin(K.c5); pin(K.c6);
-    pin(K.pio2_hi); pin(K.pio2_lo);
+    const TrigK &K = a.kconst;    // kernel-parameter constant bank: direct DFMA operands
 
     Chain ch;
     ch.integ = st[0];
@@ -356,8 +349,10 @@ __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
     }
 }
 
-cudaError_t launch_pll(const PllArgs &a, int n_captures, cudaStream_t s)
+cudaError_t launch_pll(const PllArgs &a_in, int n_captures, cudaStream_t s)
 {
+    PllArgs a = a_in;
+    a.kconst = pllcore::trig_constants();
     k_pll<<<n_captures, 32, 0, s>>>(a);
     return cudaGetLastError();
 }

@@ -105,7 +105,12 @@ struct TrigK {
             -2.75573143513906633035e-07, 2.08757232129817482790e-09,                     \
             -1.13596475577881948265e-11, 1.5707963267948966, 6.123233995736766e-17       \
     }
-FMRX_HD TrigK trig_constants()
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+static inline
+#endif
+TrigK trig_constants()
 {
     const TrigK k = FMRX_TRIGK_INIT;
     return k;

@@ -77,3 +77,25 @@ void pll_model_sincos_d(const float *x, int n, double *s, double *c)
 }
 
 }  // extern "C"
+
+// feedbackI/Q implied by (phaseEst, trigOffset): fl32(cos, sin)(fl32(w*toff + ph))
+extern "C" void pll_model_feedback(float freq, float Fs, float ph, float toff, float *fi, float *fq)
+{
+    Consts k;
+    k.kp = k.ki = 0.0f;
+    k.w = (2.0 * 3.14159265358979323846) * (double)(freq / Fs);
+    Chain c;
+    memset(&c, 0, sizeof(c));
+    c.ph = ph;
+    c.toff = toff;
+    c.fi = 1.0f;
+    chain_load(c, k);
+    if (fabsf((float)c.tad) <= FMRX_FAST_TRIG_MAX) {
+        chain_refresh(c);
+        *fi = c.fi;
+        *fq = c.fq;
+    } else {
+        *fi = (float)cos(c.tad);
+        *fq = (float)sin(c.tad);
+    }
+}
