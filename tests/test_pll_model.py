@@ -1,0 +1,100 @@
+"""The device PLL step (csrc/fmrx_pll_core.h) compiled for the HOST, against the
+oracle, bit for bit, on the CPU: the low-latency sincos / atan2 formulation and the
+group-speculative driver are exactly what k_pll runs (same header, same operations:
+IEEE fma/add/mul on both sides), so hours of signal can be checked without a GPU."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal
+
+ROOT = Path(__file__).resolve().parent.parent
+SRC = ROOT / "tests" / "pll_model.cpp"
+HDR = ROOT / "software-defined-radio-course-project_b200" / "csrc" / "fmrx_pll_core.h"
+SO = ROOT / "tests" / "_build" / "libpllmodel.so"
+f32p = C.POINTER(C.c_float)
+
+
+@pytest.fixture(scope="module")
+def model():
+    SO.parent.mkdir(exist_ok=True)
+    if not SO.exists() or SO.stat().st_mtime < max(SRC.stat().st_mtime, HDR.stat().st_mtime):
+        flags = ["-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(HDR.parent)]
+        if "fma" in Path("/proc/cpuinfo").read_text():
+            flags.append("-mfma")          # hardware fma(); libm's software fma is also exact
+        subprocess.run(["g++", *flags, "-o", str(SO), str(SRC)], check=True)
+    L = C.CDLL(str(SO))
+    L.pll_model_run.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, f32p, f32p, C.POINTER(C.c_uint)]
+    L.pll_model_sincos.argtypes = [f32p, C.c_int, f32p, f32p]
+    return L
+
+
+def run_model(L, pilot, freq, Fs, state5):
+    st = np.array(state5, np.float32)
+    trig = np.zeros(len(pilot), np.float32)
+    slow = C.c_uint(0)
+    L.pll_model_run(pilot.ctypes.data_as(f32p), len(pilot), freq, Fs, 0.01, st.ctypes.data_as(f32p),
+                    trig.ctypes.data_as(f32p), C.byref(slow))
+    return trig, st, slow.value
+
+
+def test_sincos_of_float_arguments_rounds_like_libm(model):
+    """float(sin), float(cos) over the PLL's whole argument range, 4M random floats."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([(rng.random(3_000_000) * 1.6777e7), rng.random(500_000) * 10.0,
+                        -rng.random(500_000) * 1.0e6]).astype(np.float32)
+    s = np.zeros(len(x), np.float32)
+    c = np.zeros(len(x), np.float32)
+    model.pll_model_sincos(x.ctypes.data_as(f32p), len(x), s.ctypes.data_as(f32p), c.ctypes.data_as(f32p))
+    xs = x.astype(np.float64)
+    assert np.count_nonzero(s != np.sin(xs).astype(np.float32)) <= 1
+    assert np.count_nonzero(c != np.cos(xs).astype(np.float32)) <= 1
+
+
+@pytest.mark.parametrize("mode,seed,pilot_hz", [(0, 0, 19000.0), (0, 3, 19001.5), (1, 2, 19000.0), (0, 5, 18999.2)])
+def test_fast_pll_bitwise_on_decoded_pilot(model, port, synth, mode, seed, pilot_hz):
+    info = port.mode(mode, 51)
+    nb = int(6.0 * info.rf_fs * 2 / info.block_size)
+    iq = synth.synth_iq(nb * info.block_size // 2, info.rf_fs, seed=seed, pilot_hz=pilot_hz)
+    _, d = port.chain(mode, 51).run(iq, ("pilot", "trig"))
+    trig, st, slow = run_model(model, d["pilot"], 19000.0, float(info.if_fs), [0, 0, 1, 0, 0])
+    assert_bits_equal(trig, d["trig"], "trigArg")
+    assert slow < 200            # the generic step is the exception (start-up zeros, binade changes)
+
+
+def test_fast_pll_counter_saturation_and_odd_states(model, port):
+    t = np.arange(5000, dtype=np.float64)
+    pilot = (0.1 * np.sin(2 * np.pi * 19000 / 240e3 * t)).astype(np.float32)
+    # hand-made state, inconsistent feedback pair, counter about to saturate
+    st6 = np.array([1e-4, 3.0, 0.3, -0.95, 1.0, 16777216.0 - 900.0], np.float32)
+    nco, otrig, ost = port.pll(pilot, 19000, 240e3, 2, 0, 0.01, st6)
+    trig, st, _ = run_model(model, pilot, 19000.0, 240e3, st6[[0, 1, 2, 3, 5]])
+    assert_bits_equal(trig, otrig, "trigArg through saturation")
+    assert_bits_equal(st, ost[[0, 1, 2, 3, 5]], "state through saturation")
+    assert st[4] == 16777216.0
+    # non-integer counter: the step-by-step path
+    st6 = np.array([0.0, 0.5, 1.0, 0.0, 1.0, 10.25], np.float32)
+    _, otrig, ost = port.pll(pilot[:500], 19000, 240e3, 2, 0, 0.01, st6)
+    trig, st, _ = run_model(model, pilot[:500], 19000.0, 240e3, st6[[0, 1, 2, 3, 5]])
+    assert_bits_equal(trig, otrig, "trigArg, irregular counter")
+    # zeros, negative zero, denormals, huge and NaN samples all fall back cleanly
+    x = np.array([0.0, -0.0, 1e-42, -1e-42, 1e30, -1e30, 0.3, -0.2, np.inf, 0.1, np.nan, 0.1], np.float32)
+    x = np.tile(x, 20)
+    _, otrig, ost = port.pll(x, 19000, 240e3, 2, 0, 0.01)
+    trig, st, _ = run_model(model, x, 19000.0, 240e3, [0, 0, 1, 0, 0])
+    assert_bits_equal(trig, otrig, "trigArg, degenerate samples")
+
+
+def test_fast_pll_other_loop_parameters(model, port):
+    """PLL(114000, 240000, ...) of the reference's RDS sketch: w = 2.98 rad/sample, so
+    trigArg leaves the exact-reduction range (2^24) after 5.6 M samples."""
+    t = np.arange(40000, dtype=np.float64)
+    x = (0.05 * np.sin(2 * np.pi * 114000 / 240e3 * t + 0.2)).astype(np.float32)
+    st6 = np.array([0.0, 0.0, 1.0, 0.0, 1.0, 5_600_000.0], np.float32)
+    _, otrig, ost = port.pll(x, 114000, 240e3, 0.5, 0.0, 0.01, st6)
+    trig, st, _ = run_model(model, x, 114000.0, 240e3, st6[[0, 1, 2, 3, 5]])
+    assert_bits_equal(trig, otrig, "trigArg beyond 2^24")
+    assert_bits_equal(st, ost[[0, 1, 2, 3, 5]], "state beyond 2^24")
