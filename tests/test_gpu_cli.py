@@ -1,0 +1,59 @@
+"""The host programs on the GPU: the `project` CLI (host/project_main.cpp) and the
+drop-in link of the UNMODIFIED reference main against the filter.h shim."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+CLI = ROOT / "software-defined-radio-course-project_b200" / "bin" / "project"
+DROPIN = ROOT / "oracle" / "_ref" / "project_dropin"
+
+
+def _run(exe, args, data, timeout=300):
+    return subprocess.run([str(exe), *args], input=data, capture_output=True, timeout=timeout)
+
+
+@pytest.mark.parametrize("mode,chan,taps,nblocks,extra", [(0, "2", 51, 40, 0), (0, "s", 51, 33, 4321), (1, "m", 51, 21, 0),
+                                                          (0, "1", 101, 12, 100), (2, "s", 51, 2, 0)])
+def test_cli_stdin_to_stdout_matches_oracle(fm, port, synth, mode, chan, taps, nblocks, extra):
+    assert CLI.exists(), "bin/project not built (run __graft_entry__.build())"
+    info = port.mode(mode, taps)
+    iq = synth.synth_iq(nblocks * info.block_size // 2 + extra, info.rf_fs, seed=50 + mode)
+    args = [str(mode), chan] + (["--taps", str(taps)] if taps != 51 else []) + ["--chunk-blocks", "7"]
+    r = _run(CLI, args, iq.tobytes())
+    assert r.returncode == 1                                   # the reference's exit status at EOF
+    err = r.stderr.decode()
+    label = "mono" if chan in ("1", "m") else "stereo"
+    assert f"Operating in mode {mode}, {label}" in err and "End of input stream reached!" in err
+    ref, _ = port.chain(mode, taps).run(iq)                    # channel argument changes nothing (reference quirk i)
+    out = np.frombuffer(r.stdout, np.int16)
+    assert np.array_equal(out, ref)
+
+
+def test_cli_argument_handling_like_reference(fm):
+    assert b"Invalid mode: 7!" in _run(CLI, ["7", "1"], b"").stderr
+    assert b"Invaild channel: 3!" in _run(CLI, ["0", "3"], b"").stderr
+    r = _run(CLI, ["2"], b"")                                  # a single argument is ignored -> mode 0
+    assert b"Operating in default mode 0, mono" in r.stderr and r.returncode == 1
+    assert _run(CLI, ["0", "1", "2"], b"").returncode == 1     # usage
+
+
+def test_unmodified_reference_main_links_against_the_shim(fm, port, synth):
+    """src/project.cpp (threads, queue and all) + filter_shim + iofunc_shim + libfmrx_b200:
+    its stdout is an exact prefix of the oracle PCM, short by the <=4 blocks the reference
+    itself loses at EOF."""
+    if not DROPIN.exists():
+        pytest.skip("oracle/_ref/project_dropin not built (needs the reference checkout at build time)")
+    info = port.mode(0, 51)
+    iq = synth.synth_iq(40 * info.block_size // 2, info.rf_fs, seed=77)
+    r = _run(DROPIN, ["0", "2"], iq.tobytes(), timeout=600)
+    assert r.returncode == 1 and b"End of input stream reached!" in r.stderr
+    out = np.frombuffer(r.stdout, np.int16)
+    ref, _ = port.chain(0, 51).run(iq)
+    per_block = 2 * info.audio_per_block
+    assert len(out) % per_block == 0 and 0 <= len(ref) - len(out) <= 4 * per_block and len(out) > 20 * per_block
+    assert np.array_equal(out, ref[:len(out)])
