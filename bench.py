@@ -245,8 +245,9 @@ def main_b200(args):
     iq = pkg.synth.synth_iq_torch(n_pairs, C, dev, info.rf_fs, first_station=rank * C, seed=1234 + rank)
     pcm = torch.zeros((C, n_pcm), dtype=torch.int16, device=dev)
     gathered = None
+    pcm_words = pcm.view(torch.int32)                    # one R,L frame per word (NCCL has no int16)
     if world > 1 and rank == 0:
-        gathered = [torch.empty_like(pcm) for _ in range(world)]
+        gathered = [torch.empty_like(pcm_words) for _ in range(world)]
 
     pipe = fm.Pipeline(MODE, TAPS, C, device=local)
     stream = torch.cuda.current_stream()
@@ -255,7 +256,7 @@ def main_b200(args):
         pipe.reset()
         pipe.process_device(iq.data_ptr(), iq.stride(0), nb, pcm.data_ptr(), pcm.stride(0), stream.cuda_stream)
         if world > 1:
-            dist.gather(pcm, gathered, dst=0)            # the only collective: PCM to rank 0
+            dist.gather(pcm_words, gathered, dst=0)      # the only collective: PCM to rank 0
 
     # ---- parity spot check against the oracle (first capture, first blocks) ----
     parity = "skipped"
