@@ -227,31 +227,57 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 // ============================================================================
 // The recurrence is one dependent chain per capture, so its latency bounds the
 // throughput of the whole receive chain; fmrx_pll_core.h holds the low-latency
-// formulation of one step and the measurements behind it.  One warp per capture:
-// all 32 lanes execute the same chain (no divergence).  Everything that does not
-// depend on the recurrence is produced 32 samples at a time, one lane per sample --
-// the coalesced pilot load, (double)x, the IEEE reciprocal 1/x, the half-turn flag
-// and w*trigOffset -- and parked in shared memory, from where each step fetches its
-// inputs with two broadcast LDS.128 issued one step ahead.  Steps run speculatively
-// in groups of 32 from a register checkpoint: guards only accumulate into a flag,
-// and a group with a failed guard (about one in 2000) is redone step by step with
-// the checked/generic step.  trigArg of each step is parked in shared memory by lane
-// 0 and written out coalesced per group.  Only trigArg leaves the chain; the NCO
+// formulation of one step and the measurements behind it.  One warp per capture.
+//
+// Lanes as value speculation.  The longest piece of a step is everything that hangs
+// off the new trigArg: its sin/cos (Cody-Waite + two polynomials), their float
+// roundings, the wrapped angle.  But trigArg = fl32(w*trigOffset + phaseEst) lives on
+// the float grid of its binade (spacing 2^-7 .. 0.5 rad after the first second), and
+// one loop-filter update moves phaseEst by far less than that: the new trigArg is one
+// of a handful of grid points around fl32(w*trigOffset + phaseEst_previous).  So as
+// soon as phaseEst of step t-1 is known, the 32 lanes evaluate make_feedback() for the
+// 32 grid points G_c-16 .. G_c+15 -- SIMT, the same instructions a single evaluation
+// costs -- while the chain proceeds through the atan2 shortcut and the loop filter of
+// step t.  When step t has its s = w*trigOffset + phaseEst, the grid index
+// G = rint(s/ulp) picks the lane (one DFMA, one IADD, a SHFL per word): the selected
+// values ARE make_feedback(trigArg), bit for bit.  The dependent chain per step drops
+// from ~250 to ~180 cycles: select, float products, FMA residuals, 5 DP operations,
+// conversion, loop filter, conversion.
+//
+// Everything that does not depend on the recurrence is produced 32 samples at a time,
+// one lane per sample -- the coalesced pilot load, (double)x, the IEEE reciprocal 1/x,
+// the half-turn flag and w*trigOffset -- and parked in shared memory; trigArg of each
+// step is parked there by lane 0 and written out coalesced per group.  Steps run
+// speculatively in groups of 32 from a register checkpoint: guards (x normal,
+// roundings tiny, angle clear of the +-pi seam, binade unchanged, grid point among the
+// 32 candidates) only accumulate into a flag, and a group with a failed guard is redone
+// step by step with the checked/generic step.  Only trigArg leaves the chain; the NCO
 // output cos(trigArg*scale+adjust) is evaluated in K4.
 
-struct __align__(16) PllSlot {
-    float x;
-    int turn_hi;     // high word of 2.0 (x < 0) or 0.0
-    double xd;
-    double inv_x;
-    double v;
+struct __align__(16) PllSlotA {      // per sample u
+    float x;                         // pilot sample u
+    int turn_hi_next;                // high word of 2.0/0.0 for sample u+1 (x < 0: half a turn)
+    double xd;                       // (double)x of sample u
 };
+struct __align__(16) PllSlotB {
+    double v;                        // w * trigOffset after step u (:166-167)
+    double inv_x_next;               // 1/(double)x of sample u+1, IEEE divide
+};
+
+__device__ __forceinline__ double shfl_d(double v, int src)
+{
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src),
+                            __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
 
 __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
 {
     using namespace pllcore;
-    __shared__ PllSlot s_in[2][32];
+    __shared__ PllSlotA s_a[64];     // ring of two groups, index = sample & 63
+    __shared__ PllSlotB s_b[64];
+    __shared__ double s_first[2][2]; // per group: {turn, inv_x} of its first sample
     __shared__ double s_ta[32];
+    __shared__ float4 s_cand[2][32][2];   // per candidate lane: {cf, sf, cr}, {sr, phi}
 
     const int c = blockIdx.x;
     const int lane = threadIdx.x;
@@ -263,7 +289,7 @@ __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
     k.kp = a.prm.kp;
     k.ki = a.prm.ki;
     k.w = a.prm.w;
-    const TrigK &K = a.kconst;    // kernel-parameter constant bank: direct DFMA operands
+    const TrigK &K = a.kconst;       // kernel-parameter constant bank: direct DFMA operands
 
     Chain ch;
     ch.integ = st[0];
@@ -278,53 +304,127 @@ __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
     const bool regular = toff_is_regular(ch.toff);
     const int t0 = regular ? (int)ch.toff : 0;
 
-    auto prepare = [&](int base, int buf, float pvv) {
-        PllSlot sl;
-        sl.x = pvv;
-        sl.turn_hi = (pvv < 0.0f) ? 0x40000000 : 0;
-        sl.xd = (double)pvv;
-        sl.inv_x = 1.0 / sl.xd;                                  // IEEE divide
-        const float toff = (float)min(t0 + base + lane + 1, 16777216);   // exact: <= 2^24
-        sl.v = __dmul_rn(k.w, (double)toff);                     // :167 w*trigOffset
-        s_in[buf][lane] = sl;
-    };
-
-    float pv = (lane < n) ? p[lane] : 1.0f;
-    float pvn = (32 + lane < n) ? p[32 + lane] : 1.0f;
-    prepare(0, 0, pv);
-    __syncwarp();
-
-    for (int base = 0, g = 0; base < n; base += 32, g++) {
-        const int buf = g & 1;
-        const int nn = base + 64 + lane;
-        const float pvnn = (nn < n) ? p[nn] : 1.0f;
-        prepare(base + 32, buf ^ 1, pvn);
-        const int cnt = min(32, n - base);
-        const Chain ck = ch;
-        bool good = regular;
-        if (good) {
-            const float4 *slots = reinterpret_cast<const float4 *>(&s_in[buf][0]);
-            float4 q0 = slots[0], q1 = slots[1];
-            for (int t = 0; t < cnt; t++) {
-                const int tn = (t + 1) & 31;
-                const float4 n0 = slots[2 * tn], n1 = slots[2 * tn + 1];   // next step's inputs
-                StepIn in;
-                in.x = q0.x;
-                in.turn = __hiloint2double(__float_as_int(q0.y), 0);
-                in.xd = __hiloint2double(__float_as_int(q0.w), __float_as_int(q0.z));
-                in.inv_x = __hiloint2double(__float_as_int(q1.y), __float_as_int(q1.x));
-                in.v = __hiloint2double(__float_as_int(q1.w), __float_as_int(q1.z));
-                good &= chain_step_spec(ch, k, K, in);
-                if (lane == 0)
-                    s_ta[t] = ch.tad;
-                q0 = n0;
-                q1 = n1;
+    // one lane per sample: off-chain inputs of sample base+lane into the ring
+    auto prepare = [&](int base, float pvv) {
+        const int u = (base + lane) & 63;
+        const double xd = (double)pvv;
+        const double inv = 1.0 / xd;                                  // IEEE divide
+        const int turn_hi = (pvv < 0.0f) ? 0x40000000 : 0;
+        const float toff = (float)min(t0 + base + lane + 1, 16777216);    // exact: <= 2^24
+        s_a[u].x = pvv;
+        s_a[u].xd = xd;
+        s_b[u].v = __dmul_rn(k.w, (double)toff);
+        // turn / reciprocal are consumed one sample early (with the feedback prepared for it)
+        if (lane > 0) {
+            s_a[(u - 1) & 63].turn_hi_next = turn_hi;
+            s_b[(u - 1) & 63].inv_x_next = inv;
+        } else {
+            s_first[(base >> 5) & 1][0] = __hiloint2double(turn_hi, 0);
+            s_first[(base >> 5) & 1][1] = inv;
+            if (base > 0) {
+                s_a[(u - 1) & 63].turn_hi_next = turn_hi;
+                s_b[(u - 1) & 63].inv_x_next = inv;
             }
         }
-        if (!good) {
-            ch = ck;
+    };
+
+    float pvn = (lane < n) ? p[lane] : 1.0f;
+    prepare(0, pvn);
+    pvn = (32 + lane < n) ? p[32 + lane] : 1.0f;
+    bool stale = false;              // ch's sincos leftovers lag behind ch.tad (after speculative groups)
+    int n_groups = 0, n_redone = 0;  // diagnostics: state[6], state[7]
+    const double lane_off = (double)(lane - 16);
+
+    for (int base = 0; base < n; base += 32) {
+        const int nn = base + 64 + lane;
+        const float pvnn = (nn < n) ? p[nn] : 1.0f;
+        prepare(base + 32, pvn);
+        __syncwarp();
+        const int cnt = min(32, n - base);
+        const Chain ck = ch;
+        bool good = regular && ch.binade != FMRX_DISARMED;
+        if (good) {
+            const double ulp = ch.ulp, inv_ulp = ch.inv_ulp;
+            const unsigned binade = ch.binade;
+            float integ = ch.integ, ph = ch.ph;
+            const int g = (base >> 5) & 1;
+            // The loop is rotated so that the two activities of an iteration depend only on
+            // the previous iteration and can be interleaved by the scheduler:
+            //   A: pick the candidate that is trigArg(t-1) -> feedback of sample t -> atan2
+            //      shortcut and loop filter of sample t -> s(t), phaseEst(t)
+            //   B: from phaseEst(t-1), the 32 candidates for trigArg(t), combined with the
+            //      inputs of sample t+1
+            // "candidates" for trigArg(base-1), which is known: every lane holds the real one
+            // "candidates" for trigArg(base-1), which is known: every lane holds the real one
+            {
+                const Feedback f0 = make_feedback(K, ch.tad, s_first[g][0], s_first[g][1], nullptr, nullptr);
+                s_cand[1][lane][0] = make_float4(f0.cf, f0.sf, __int_as_float(__double2loint(f0.cr)),
+                                                 __int_as_float(__double2hiint(f0.cr)));
+                s_cand[1][lane][1] = make_float4(__int_as_float(__double2loint(f0.sr)), __int_as_float(__double2hiint(f0.sr)),
+                                                 __int_as_float(__double2loint(f0.phi)), __int_as_float(__double2hiint(f0.phi)));
+            }
+            double q = FMRX_RINT_MAGIC;          // grid_index(q) - gc + 16 == 16
+            int gc = 0;
+            double phd = (double)ph;
+            double inv_x = s_first[g][1];        // 1/x of the sample about to run
             for (int t = 0; t < cnt; t++) {
-                const float ta = chain_step(ch, k, K, s_in[buf][t].x, nullptr);
+                const PllSlotA sa = s_a[(base + t) & 63];
+                const PllSlotB sb = s_b[(base + t) & 63];
+                __syncwarp();                    // candidate table of the previous iteration is complete
+                // ---- A: the candidate that IS trigArg(t-1): two broadcast LDS.128 ----
+                const int idx = grid_index(q) - gc + 16;
+                const int src = idx & 31;
+                const float4 c0 = s_cand[(t + 1) & 1][src][0];
+                const float4 c1 = s_cand[(t + 1) & 1][src][1];
+                Feedback fb;
+                fb.cf = c0.x;
+                fb.sf = c0.y;
+                fb.cr = __hiloint2double(__float_as_int(c0.w), __float_as_int(c0.z));
+                fb.sr = __hiloint2double(__float_as_int(c1.y), __float_as_int(c1.x));
+                fb.phi = __hiloint2double(__float_as_int(c1.w), __float_as_int(c1.z));
+                fb.csx = p_mul(fb.cr, inv_x);
+                fb.snx = p_mul(fb.sr, inv_x);
+                // ---- B (uses phaseEst of the previous step only): candidates for trigArg(t),
+                //      with the wrapped angle already turned for sample t+1 ----
+                const double qc = grid_round(p_add(sb.v, phd), inv_ulp);
+                gc = grid_index(qc);
+                {
+                    const Feedback f = make_feedback(K, grid_value(p_add(qc, lane_off), ulp),
+                                                     __hiloint2double(sa.turn_hi_next, 0), 1.0, nullptr, nullptr);
+                    s_cand[t & 1][lane][0] = make_float4(f.cf, f.sf, __int_as_float(__double2loint(f.cr)),
+                                                         __int_as_float(__double2hiint(f.cr)));
+                    s_cand[t & 1][lane][1] = make_float4(__int_as_float(__double2loint(f.sr)), __int_as_float(__double2hiint(f.sr)),
+                                                         __int_as_float(__double2loint(f.phi)), __int_as_float(__double2hiint(f.phi)));
+                }
+                // ---- A continued ----
+                bool ok = (unsigned)idx < 32u;
+                const double s = step_front(k, fb, sa.x, sa.xd, sb.v, integ, ph, phd, ok);
+                q = grid_round(s, inv_ulp);
+                good &= ok && in_binade(s, binade);
+                if (lane == 0)
+                    s_ta[t] = grid_value(q, ulp);
+                inv_x = sb.inv_x_next;
+            }
+            // the last trigArg must be one of its candidates too (checked like the others)
+            good &= (unsigned)(grid_index(q) - gc + 16) < 32u;
+            if (good) {
+                ch.integ = integ;
+                ch.ph = ph;
+                ch.toff = (float)min(t0 + base + cnt, 16777216);
+                ch.tad = grid_value(q, ulp);
+                stale = true;
+            }
+        }
+        n_groups++;
+        if (!good) {
+            n_redone++;
+            ch = ck;
+            if (stale) {             // bring the sincos leftovers up to date with ch.tad
+                chain_refresh(ch);
+                stale = false;
+            }
+            for (int t = 0; t < cnt; t++) {
+                const float ta = chain_step(ch, k, K, s_a[(base + t) & 63].x, nullptr);
                 if (lane == 0)
                     s_ta[t] = (double)ta;
             }
@@ -333,10 +433,11 @@ __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
         if (lane < cnt)
             tr[base + lane] = __double2float_rn(s_ta[lane]);
         __syncwarp();
-        pv = pvn;
         pvn = pvnn;
     }
     if (lane == 0) {
+        if (stale)
+            chain_refresh(ch);
         float fi, fq;
         chain_feedback(ch, fi, fq);
         st[0] = ch.integ;
@@ -344,6 +445,8 @@ __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
         st[2] = fi;
         st[3] = fq;
         st[5] = ch.toff;
+        st[6] = (float)n_groups;     // diagnostics of the last launch
+        st[7] = (float)n_redone;
         if (n > 0)
             st[4] = nco_from_trig(__double2float_rn(ch.tad), a.prm.scale, a.prm.adjust);   // :173
     }

@@ -201,11 +201,12 @@ struct Chain {
     float cf, sf;        // fl32(cos r), fl32(sin r): the unrotated feedback pair
     double cr, sr;       // cos r, sin r
     double r, nd;        // ta = r + nd*pi/2
-    // trigArg = fl32(w*toff + ph) is rounded in double as (s + magic) - magic, which
-    // is the float rounding while |s| stays in the binade whose exponent field is
-    // `binade` (high word of 2^e).  FMRX_DISARMED switches the fast step off: the
-    // generic step runs and re-arms it.
-    double magic;
+    // trigArg = fl32(w*toff + ph): while |s| stays in the binade whose exponent field
+    // is `binade` (high word of 2^e) the float grid there has spacing ulp = 2^(e-23),
+    // so the float rounding is G = rint(s/ulp) (add-magic trick, low word = G) and
+    // trigArg = G*ulp, all exact in double.  FMRX_DISARMED switches the fast step off:
+    // the generic step runs and re-arms it.
+    double ulp, inv_ulp;
     unsigned binade;
 };
 
@@ -218,10 +219,11 @@ FMRX_HD void chain_arm(Chain &c)
         int e;
         (void)frexpf(at, &e);                 // at = m * 2^e, m in [0.5, 1)
         c.binade = (unsigned)(e - 1 + 1023) << 20;
-        c.magic = ldexp(1.5, e - 1 + 29);
+        c.ulp = ldexp(1.0, e - 1 - 23);
+        c.inv_ulp = ldexp(1.0, 23 - (e - 1));
     } else {
         c.binade = FMRX_DISARMED;
-        c.magic = 0.0;
+        c.ulp = c.inv_ulp = 0.0;
     }
 }
 
@@ -256,7 +258,7 @@ FMRX_HD void chain_load(Chain &c, const Consts &k)
     const float fi = c.fi, fq = c.fq;
     const float ta = p_d2f(p_add(p_mul(k.w, (double)c.toff), (double)c.ph));
     c.tad = (double)ta;
-    c.cr = c.sr = c.r = c.nd = c.magic = 0.0;
+    c.cr = c.sr = c.r = c.nd = c.ulp = c.inv_ulp = 0.0;
     c.cf = c.sf = 0.0f;
     c.binade = FMRX_DISARMED;
     if (!(fabsf(ta) <= FMRX_FAST_TRIG_MAX))
@@ -312,38 +314,97 @@ FMRX_HD StepIn step_inputs(const Consts &k, float x, float toff_after)
     return in;
 }
 
-// The speculative fast step: ALWAYS updates the state, through the low-latency
-// formulation, and returns whether every guard held.  When it returns false the
-// state is garbage and the caller must restore a checkpoint (k_pll checkpoints
-// once per 32 steps and redoes the group step by step).  No guard sits on the
-// dependent chain.
-FMRX_HD bool chain_step_spec(Chain &c, const Consts &k, const TrigK &K, const StepIn &in)
+// What the atan2 shortcut and the float products of ONE sample need from the trigArg
+// that precedes it: the unrotated feedback pair and its double leftovers, already
+// combined with that sample's off-chain inputs (1/x and its half-turn).
+struct Feedback {
+    float cf, sf;        // fl32(cos r), fl32(sin r)
+    double cr, sr;       // cos r, sin r
+    double csx, snx;     // cos r / x, sin r / x
+    double phi;          // trigArg wrapped to (-pi, pi], half a turn more when x < 0
+};
+
+// Everything a sample needs from the preceding trigArg `tad` (a float value in a
+// double, |tad| <= 2^24).  On the device every lane evaluates this for a different
+// CANDIDATE trigArg before the loop filter has decided which one it is.
+FMRX_HD Feedback make_feedback(const TrigK &K, double tad, double turn, double inv_x, double *r_out,
+                               double *nd_out)
 {
-    // ---- atan2(eq, ei) = -(phi + delta), in the unrotated frame --------------------
-    const double phi = wrapped_angle(K, p_add(c.nd, in.turn), c.r);
-    const double csx = p_mul(c.cr, in.inv_x);
-    const double snx = p_mul(c.sr, in.inv_x);
-    const float ei = p_fmulf(in.x, c.cf);                            // :159 (up to the quadrant)
-    const float eq = p_fmulf(in.x, -c.sf);                           // :160
-    const double ti = p_fma(-in.xd, c.cr, (double)ei);   // exact rounding residuals, rounded once
-    const double tq = p_fma(in.xd, c.sr, (double)eq);
-    const double m1 = p_mul(csx, tq);
-    const double cross = -p_fma(snx, ti, m1);                  // rotation by the roundings
-    const double dotc = p_fma(-snx, tq, p_mul(csx, ti));       // radial part (second order)
-    const double a1 = p_fma(-snx, ti, p_add(phi, -m1));        // phi + cross
+    Feedback f;
+    double r, nd;
+    sincos_reduced(K, tad, f.sr, f.cr, r, nd);
+    f.sf = p_d2f(f.sr);                                              // :168-169 (up to the quadrant)
+    f.cf = p_d2f(f.cr);
+    f.phi = wrapped_angle(K, p_add(nd, turn), r);
+    f.csx = p_mul(f.cr, inv_x);
+    f.snx = p_mul(f.sr, inv_x);
+    if (r_out) {
+        *r_out = r;
+        *nd_out = nd;
+    }
+    return f;
+}
+
+// atan2 + loop filter of one sample (:159-167): updates integ, ph and returns
+// s = w*trigOffset + phaseEst in double (the value the reference then stores to a
+// float).  `ok` is cleared if a guard of the atan2 shortcut fails.
+FMRX_HD double step_front(const Consts &k, const Feedback &f, float x, double xd, double v, float &integ,
+                          float &ph, double &phd, bool &ok)
+{
+    const float ei = p_fmulf(x, f.cf);                               // :159 (up to the quadrant)
+    const float eq = p_fmulf(x, -f.sf);                              // :160
+    const double ti = p_fma(-xd, f.cr, (double)ei);   // exact rounding residuals, rounded once
+    const double tq = p_fma(xd, f.sr, (double)eq);
+    const double m1 = p_mul(f.csx, tq);
+    const double cross = -p_fma(f.snx, ti, m1);                // rotation by the roundings
+    const double dotc = p_fma(-f.snx, tq, p_mul(f.csx, ti));   // radial part (second order)
+    const double a1 = p_fma(-f.snx, ti, p_add(f.phi, -m1));    // phi + cross
     const double alpha = p_fma(-cross, dotc, a1);              // phi + cross*(1 - dotc)
     const float ed = p_d2f(-alpha);                                  // :161
-    bool ok = fabs(cross) < 0x1p-20 && fabs(dotc) < 0x1p-20 && fabs(phi) < 3.125;
+    ok = ok && fabs(cross) < 0x1p-20 && fabs(dotc) < 0x1p-20 && fabs(f.phi) < 3.125;
+    integ = p_faddf(integ, p_fmulf(k.ki, ed));                       // :163
+    ph = p_faddf(ph, p_faddf(p_fmulf(k.kp, ed), integ));             // :164
+    phd = (double)ph;
+    return p_add(v, phd);                                            // :167 in double
+}
 
-    // ---- loop filter (float, the reference's order) --------------------------------
-    c.integ = p_faddf(c.integ, p_fmulf(k.ki, ed));                   // :163
-    c.ph = p_faddf(c.ph, p_faddf(p_fmulf(k.kp, ed), c.integ));       // :164
+// rint(s/ulp) as a double holding an integer plus the magic constant: its low word is
+// the grid index G (two's complement), (q - magic)*ulp is the float-rounded value.
+FMRX_HD double grid_round(double s, double inv_ulp) { return p_fma(s, inv_ulp, FMRX_RINT_MAGIC); }
+FMRX_HD int grid_index(double q)
+{
+#if defined(__CUDACC__)
+    return __double2loint(q);
+#else
+    uint64_t u;
+    memcpy(&u, &q, sizeof(u));
+    return (int)(uint32_t)u;
+#endif
+}
+FMRX_HD double grid_value(double q, double ulp) { return p_mul(p_add(q, -FMRX_RINT_MAGIC), ulp); }
+FMRX_HD bool in_binade(double s, unsigned binade)
+{
+    return (((unsigned)p_hi32(s) & 0x7fffffffu) - binade) < 0x00100000u;
+}
+
+// The speculative fast step, composed sequentially: ALWAYS updates the state and
+// returns whether every guard held.  When it returns false the state is garbage and
+// the caller must restore a checkpoint.  (k_pll runs the same pieces with the
+// make_feedback() of the NEXT sample evaluated by the 32 lanes for 32 candidate
+// trigArgs ahead of time; the values it ends up using are exactly these.)
+FMRX_HD bool chain_step_spec(Chain &c, const Consts &k, const TrigK &K, const StepIn &in)
+{
+    Feedback f;
+    f.cf = c.cf; f.sf = c.sf; f.cr = c.cr; f.sr = c.sr;
+    f.phi = wrapped_angle(K, p_add(c.nd, in.turn), c.r);
+    f.csx = p_mul(c.cr, in.inv_x);
+    f.snx = p_mul(c.sr, in.inv_x);
+    bool ok = true;
+    double phd;
+    const double s = step_front(k, f, in.x, in.xd, in.v, c.integ, c.ph, phd, ok);
     c.toff = p_faddf(c.toff, 1.0f);                                  // :166
-    const double s = p_add(in.v, (double)c.ph);                      // :167 in double ...
-    ok = ok && (((unsigned)p_hi32(s) & 0x7fffffffu) - c.binade) < 0x00100000u;
-    c.tad = p_add(p_add(s, c.magic), -c.magic);                      // ... stored to float
-
-    // ---- sin, cos of the new trigArg -----------------------------------------------
+    ok = ok && in_binade(s, c.binade);
+    c.tad = grid_value(grid_round(s, c.inv_ulp), c.ulp);             // :167 stored to float
     sincos_reduced(K, c.tad, c.sr, c.cr, c.r, c.nd);
     c.sf = p_d2f(c.sr);                                              // :168-169 (up to the quadrant)
     c.cf = p_d2f(c.cr);

@@ -44,4 +44,7 @@ for r in range(a.reps):
            "wall_ms": (time.perf_counter() - t0) * 1e3,
            "iq_msps": C * nb * info.block_size / 2 / ms / 1e3,
            "pll_ns_per_sample": t["pll_ms"] * 1e6 / n_if, **t}
+    import struct
+    blob = p.get_state(0)
+    out["pll_groups_last_chunk"], out["pll_groups_redone_last_chunk"] = struct.unpack("<2f", blob[-8:])
     print(json.dumps(out))
