@@ -227,63 +227,102 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 // ============================================================================
 // The recurrence is one dependent chain per capture, so its latency bounds the
 // throughput of the whole receive chain; fmrx_pll_core.h holds the low-latency
-// formulation of one step and the measurements behind it.  One warp per capture.
+// formulation of one step and the measurements behind it.  One CTA of eight warps per
+// capture, every warp SIMT-uniform or one-lane-per-item:
 //
-// Lanes as value speculation.  The longest piece of a step is everything that hangs
-// off the new trigArg: its sin/cos (Cody-Waite + two polynomials), their float
-// roundings, the wrapped angle.  But trigArg = fl32(w*trigOffset + phaseEst) lives on
-// the float grid of its binade (spacing 2^-7 .. 0.5 rad after the first second), and
-// one loop-filter update moves phaseEst by far less than that: the new trigArg is one
-// of a handful of grid points around fl32(w*trigOffset + phaseEst_previous).  So as
-// soon as phaseEst of step t-1 is known, the 32 lanes evaluate make_feedback() for the
-// 32 grid points G_c-16 .. G_c+15 -- SIMT, the same instructions a single evaluation
-// costs -- while the chain proceeds through the atan2 shortcut and the loop filter of
-// step t.  When step t has its s = w*trigOffset + phaseEst, the grid index
-// G = rint(s/ulp) picks the lane (one DFMA, one IADD, a SHFL per word): the selected
-// values ARE make_feedback(trigArg), bit for bit.  The dependent chain per step drops
-// from ~250 to ~180 cycles: select, float products, FMA residuals, 5 DP operations,
-// conversion, loop filter, conversion.
+//   warp 0  the chain, reduced to what is irreducibly sequential: the four float
+//           operations of the loop filter, the conversion of phaseEst to double, the sum
+//           s = w*trigOffset + phaseEst, its grid index G = rint(s/ulp) -- and then a
+//           TABLE LOOKUP of the next phase-detector output.  About 95 dependent cycles.
+//   warps 1-3, 5-7  value speculation.  trigArg(u) = fl32(s) lives on the float grid of
+//           its binade (spacing 2^-7 .. 0.5 rad after the first second) and a few
+//           loop-filter updates move phaseEst by far less than that, so trigArg(u) is one
+//           of a handful of grid points around rint((w*trigOffset(u) + phaseEst(u-L))/ulp).
+//           As soon as warp 0 publishes phaseEst(u-L), the 32 lanes of a candidate warp
+//           evaluate, for the 32 grid points G_c-16 .. G_c+15, everything that hangs off
+//           trigArg(u): sin/cos (Cody-Waite + two polynomials), their float roundings, the
+//           wrapped angle, the float products with pilot sample u+1, the FMA residuals and
+//           the atan2 shortcut -- i.e. errorD(u+1) = fl32(atan2(eQ, eI)) of the NEXT sample
+//           for each candidate (SIMT: the instructions of a single evaluation).  The entry
+//           warp 0 picks is bit for bit what the sequential formulation computes.
+//   warp 4  I/O.  One lane per sample: the coalesced pilot load, (double)x, the IEEE
+//           reciprocal 1/x, the half-turn flag and w*trigOffset for the group after next
+//           into a 4-group ring in shared memory; and the coalesced store of the previous
+//           group's trigArg.
 //
-// Everything that does not depend on the recurrence is produced 32 samples at a time,
-// one lane per sample -- the coalesced pilot load, (double)x, the IEEE reciprocal 1/x,
-// the half-turn flag and w*trigOffset -- and parked in shared memory; trigArg of each
-// step is parked there by lane 0 and written out coalesced per group.  Steps run
-// speculatively in groups of 32 from a register checkpoint: guards (x normal,
-// roundings tiny, angle clear of the +-pi seam, binade unchanged, grid point among the
-// 32 candidates) only accumulate into a flag, and a group with a failed guard is redone
-// step by step with the checked/generic step.  Only trigArg leaves the chain; the NCO
-// output cos(trigArg*scale+adjust) is evaluated in K4.
+// Hand-off is through shared memory with sequence-tagged 16-byte records written by one
+// store (phaseEst from warp 0; table headers from the candidate warps after a block
+// fence) and bounded polling -- no barrier inside a group.  Steps run in groups from a
+// register checkpoint: guards (x normal, roundings tiny, angle clear of the +-pi seam,
+// binade unchanged, grid point among the 32 candidates, table on time) only accumulate
+// into a flag, and a group with a failed guard is redone by warp 0 alone with the
+// checked/generic step; after a failure the next groups run checked directly and
+// speculation is retried with exponential back-off (the first fraction of a second of
+// a capture, where the float grid is finer than the loop's own jitter, runs checked).
+// Only trigArg leaves the chain; the NCO output cos(trigArg*scale+adjust) is evaluated
+// in K4.
 
-struct __align__(16) PllSlotA {      // per sample u
-    float x;                         // pilot sample u
-    int turn_hi_next;                // high word of 2.0/0.0 for sample u+1 (x < 0: half a turn)
-    double xd;                       // (double)x of sample u
-};
-struct __align__(16) PllSlotB {
-    double v;                        // w * trigOffset after step u (:166-167)
-    double inv_x_next;               // 1/(double)x of sample u+1, IEEE divide
+constexpr int PLL_WARPS = 8;
+constexpr int PLL_THREADS = 32 * PLL_WARPS;
+constexpr int PLL_CAND_WARPS = 6;        // warps 1,2,3,5,6,7
+constexpr int PLL_IO_WARP = 4;           // shares a scheduler with warp 0 but is idle most of the time
+constexpr int PLL_GROUP = 128;           // steps between checkpoints / barriers
+constexpr int PLL_RING = 4 * PLL_GROUP;  // per-sample input ring: 4 groups
+constexpr int PLL_TABLES = 16;           // candidate tables / phaseEst records in flight
+constexpr int PLL_LOOKBACK = 8;          // candidates for trigArg(u) are centred on phaseEst(u - PLL_LOOKBACK)
+constexpr int PLL_SPIN_LIMIT = 1 << 16;  // bounded polling (~1 ms): a bug must not hang the GPU
+
+struct __align__(16) PllIn {             // off-chain inputs of one sample
+    float x;
+    int turn_hi;                         // high word of 2.0 (x < 0: half a turn) or 0.0
+    double xd;                           // (double)x
+    double inv_x;                        // 1/(double)x, IEEE divide
+    double v;                            // w * trigOffset after this step (:166-167)
 };
 
-__device__ __forceinline__ double shfl_d(double v, int src)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_v4(void *p, int a, int b, int c, int d)
 {
-    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src),
-                            __shfl_sync(0xffffffffu, __double2loint(v), src));
+    asm volatile("st.volatile.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
 }
+__device__ __forceinline__ int4 ld_v4(const void *p)
+{
+    int4 v;
+    asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(smem_u32(p))
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ int2 ld_v2(const void *p)
+{
+    int2 v;
+    asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ double i2d(int hi, int lo) { return __hiloint2double(hi, lo); }
 
-__global__ void __launch_bounds__(32) k_pll(const PllArgs a)
+__global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
 {
     using namespace pllcore;
-    __shared__ PllSlotA s_a[64];     // ring of two groups, index = sample & 63
-    __shared__ PllSlotB s_b[64];
-    __shared__ double s_first[2][2]; // per group: {turn, inv_x} of its first sample
-    __shared__ double s_ta[32];
-    __shared__ float4 s_cand[2][32][2];   // per candidate lane: {cf, sf, cr}, {sr, phi}
+    __shared__ PllIn s_in[PLL_RING];
+    __shared__ int4 s_ph[PLL_TABLES];                 // {phaseEst lo, hi, seq, -}: published by warp 0
+    // candidate tables, indexed by (step & 15, grid index & 31): {errorD of the next sample, grid
+    // index, step+1 (negated if a guard failed), -}; one self-validating 16-byte record per lane
+    __shared__ int4 s_tab[PLL_TABLES][32];
+    __shared__ int s_g[2][PLL_GROUP];                 // grid index of each trigArg of the group, double-buffered
+    __shared__ double s_grid[2];                      // ulp, 1/ulp of the current group
+    __shared__ double s_ulp_hist[2];                  // ulp the parked grid indices of a group refer to
+    __shared__ int s_spec[2];                         // 1: s_g holds grid indices, 0: float bit patterns
+    __shared__ int s_flag[4];                         // [0] group runs speculatively, [1] error
 
     const int c = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float *p = a.pilot + (size_t)c * a.pilot_stride;
     float *tr = a.trig + (size_t)c * a.if_stride + a.if_off;
     float *st = a.state + 8 * (size_t)c;
+    const int n = a.n_if;
 
     Consts k;
     k.kp = a.prm.kp;
@@ -291,151 +330,226 @@ __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
     k.w = a.prm.w;
     const TrigK &K = a.kconst;       // kernel-parameter constant bank: direct DFMA operands
 
-    Chain ch;
-    ch.integ = st[0];
-    ch.ph = st[1];
-    ch.fi = st[2];
-    ch.fq = st[3];
-    ch.toff = st[5];
-    chain_load(ch, k);
-    const int n = a.n_if;
+    // every warp derives the (uniform) start of the trigOffset sequence itself
+    const float toff0 = st[5];
+    const bool regular = toff_is_regular(toff0);
+    const int t0 = regular ? (int)toff0 : 0;
+    // candidate warps: 1,2,3,5,6,7 -> 0..5
+    const int cand_id = (warp < PLL_IO_WARP) ? warp - 1 : warp - 2;
 
-    // trigOffset after j steps is min(t0 + j, 2^24) when it starts integer-valued
-    const bool regular = toff_is_regular(ch.toff);
-    const int t0 = regular ? (int)ch.toff : 0;
-
-    // one lane per sample: off-chain inputs of sample base+lane into the ring
-    auto prepare = [&](int base, float pvv) {
-        const int u = (base + lane) & 63;
-        const double xd = (double)pvv;
-        const double inv = 1.0 / xd;                                  // IEEE divide
-        const int turn_hi = (pvv < 0.0f) ? 0x40000000 : 0;
-        const float toff = (float)min(t0 + base + lane + 1, 16777216);    // exact: <= 2^24
-        s_a[u].x = pvv;
-        s_a[u].xd = xd;
-        s_b[u].v = __dmul_rn(k.w, (double)toff);
-        // turn / reciprocal are consumed one sample early (with the feedback prepared for it)
-        if (lane > 0) {
-            s_a[(u - 1) & 63].turn_hi_next = turn_hi;
-            s_b[(u - 1) & 63].inv_x_next = inv;
-        } else {
-            s_first[(base >> 5) & 1][0] = __hiloint2double(turn_hi, 0);
-            s_first[(base >> 5) & 1][1] = inv;
-            if (base > 0) {
-                s_a[(u - 1) & 63].turn_hi_next = turn_hi;
-                s_b[(u - 1) & 63].inv_x_next = inv;
-            }
+    // I/O warp: one lane per sample, off-chain inputs of the samples of a group into the ring
+    auto prepare = [&](int base) {
+        for (int j = 0; j < PLL_GROUP; j += 32) {
+            const int u = base + j + lane;
+            const float pvv = (u < n) ? p[u] : 1.0f;
+            PllIn in;
+            in.x = pvv;
+            in.turn_hi = (pvv < 0.0f) ? 0x40000000 : 0;
+            in.xd = (double)pvv;
+            in.inv_x = 1.0 / in.xd;                                      // IEEE divide
+            const float toff = (float)min(t0 + u + 1, 16777216);         // exact: <= 2^24
+            in.v = __dmul_rn(k.w, (double)toff);
+            s_in[u & (PLL_RING - 1)] = in;
         }
     };
 
-    float pvn = (lane < n) ? p[lane] : 1.0f;
-    prepare(0, pvn);
-    pvn = (32 + lane < n) ? p[32 + lane] : 1.0f;
-    bool stale = false;              // ch's sincos leftovers lag behind ch.tad (after speculative groups)
-    int n_groups = 0, n_redone = 0;  // diagnostics: state[6], state[7]
-    const double lane_off = (double)(lane - 16);
-
-    for (int base = 0; base < n; base += 32) {
-        const int nn = base + 64 + lane;
-        const float pvnn = (nn < n) ? p[nn] : 1.0f;
-        prepare(base + 32, pvn);
-        __syncwarp();
-        const int cnt = min(32, n - base);
-        const Chain ck = ch;
-        bool good = regular && ch.binade != FMRX_DISARMED;
-        if (good) {
-            const double ulp = ch.ulp, inv_ulp = ch.inv_ulp;
-            const unsigned binade = ch.binade;
-            float integ = ch.integ, ph = ch.ph;
-            const int g = (base >> 5) & 1;
-            // The loop is rotated so that the two activities of an iteration depend only on
-            // the previous iteration and can be interleaved by the scheduler:
-            //   A: pick the candidate that is trigArg(t-1) -> feedback of sample t -> atan2
-            //      shortcut and loop filter of sample t -> s(t), phaseEst(t)
-            //   B: from phaseEst(t-1), the 32 candidates for trigArg(t), combined with the
-            //      inputs of sample t+1
-            // "candidates" for trigArg(base-1), which is known: every lane holds the real one
-            // "candidates" for trigArg(base-1), which is known: every lane holds the real one
-            {
-                const Feedback f0 = make_feedback(K, ch.tad, s_first[g][0], s_first[g][1], nullptr, nullptr);
-                s_cand[1][lane][0] = make_float4(f0.cf, f0.sf, __int_as_float(__double2loint(f0.cr)),
-                                                 __int_as_float(__double2hiint(f0.cr)));
-                s_cand[1][lane][1] = make_float4(__int_as_float(__double2loint(f0.sr)), __int_as_float(__double2hiint(f0.sr)),
-                                                 __int_as_float(__double2loint(f0.phi)), __int_as_float(__double2hiint(f0.phi)));
-            }
-            double q = FMRX_RINT_MAGIC;          // grid_index(q) - gc + 16 == 16
-            int gc = 0;
-            double phd = (double)ph;
-            double inv_x = s_first[g][1];        // 1/x of the sample about to run
-            for (int t = 0; t < cnt; t++) {
-                const PllSlotA sa = s_a[(base + t) & 63];
-                const PllSlotB sb = s_b[(base + t) & 63];
-                __syncwarp();                    // candidate table of the previous iteration is complete
-                // ---- A: the candidate that IS trigArg(t-1): two broadcast LDS.128 ----
-                const int idx = grid_index(q) - gc + 16;
-                const int src = idx & 31;
-                const float4 c0 = s_cand[(t + 1) & 1][src][0];
-                const float4 c1 = s_cand[(t + 1) & 1][src][1];
-                Feedback fb;
-                fb.cf = c0.x;
-                fb.sf = c0.y;
-                fb.cr = __hiloint2double(__float_as_int(c0.w), __float_as_int(c0.z));
-                fb.sr = __hiloint2double(__float_as_int(c1.y), __float_as_int(c1.x));
-                fb.phi = __hiloint2double(__float_as_int(c1.w), __float_as_int(c1.z));
-                fb.csx = p_mul(fb.cr, inv_x);
-                fb.snx = p_mul(fb.sr, inv_x);
-                // ---- B (uses phaseEst of the previous step only): candidates for trigArg(t),
-                //      with the wrapped angle already turned for sample t+1 ----
-                const double qc = grid_round(p_add(sb.v, phd), inv_ulp);
-                gc = grid_index(qc);
-                {
-                    const Feedback f = make_feedback(K, grid_value(p_add(qc, lane_off), ulp),
-                                                     __hiloint2double(sa.turn_hi_next, 0), 1.0, nullptr, nullptr);
-                    s_cand[t & 1][lane][0] = make_float4(f.cf, f.sf, __int_as_float(__double2loint(f.cr)),
-                                                         __int_as_float(__double2hiint(f.cr)));
-                    s_cand[t & 1][lane][1] = make_float4(__int_as_float(__double2loint(f.sr)), __int_as_float(__double2hiint(f.sr)),
-                                                         __int_as_float(__double2loint(f.phi)), __int_as_float(__double2hiint(f.phi)));
-                }
-                // ---- A continued ----
-                bool ok = (unsigned)idx < 32u;
-                const double s = step_front(k, fb, sa.x, sa.xd, sb.v, integ, ph, phd, ok);
-                q = grid_round(s, inv_ulp);
-                good &= ok && in_binade(s, binade);
-                if (lane == 0)
-                    s_ta[t] = grid_value(q, ulp);
-                inv_x = sb.inv_x_next;
-            }
-            // the last trigArg must be one of its candidates too (checked like the others)
-            good &= (unsigned)(grid_index(q) - gc + 16) < 32u;
-            if (good) {
-                ch.integ = integ;
-                ch.ph = ph;
-                ch.toff = (float)min(t0 + base + cnt, 16777216);
-                ch.tad = grid_value(q, ulp);
-                stale = true;
-            }
-        }
-        n_groups++;
-        if (!good) {
-            n_redone++;
-            ch = ck;
-            if (stale) {             // bring the sincos leftovers up to date with ch.tad
-                chain_refresh(ch);
-                stale = false;
-            }
-            for (int t = 0; t < cnt; t++) {
-                const float ta = chain_step(ch, k, K, s_a[(base + t) & 63].x, nullptr);
-                if (lane == 0)
-                    s_ta[t] = (double)ta;
-            }
-        }
-        __syncwarp();
-        if (lane < cnt)
-            tr[base + lane] = __double2float_rn(s_ta[lane]);
-        __syncwarp();
-        pvn = pvnn;
+    if (threadIdx.x < PLL_TABLES)
+        s_ph[threadIdx.x] = make_int4(0, 0, (int)0x80000000, 0);
+    for (int i = threadIdx.x; i < PLL_TABLES * 32; i += PLL_THREADS)
+        s_tab[i >> 5][i & 31] = make_int4(0, 0, (int)0x80000000, 0);
+    if (threadIdx.x == 0)
+        s_flag[1] = 0;
+    if (warp == PLL_IO_WARP) {
+        prepare(0);
+        prepare(PLL_GROUP);
     }
-    if (lane == 0) {
+
+    // warp 0 owns the recurrence state
+    Chain ch;
+    bool stale = false;              // ch's sincos leftovers lag behind ch.tad (after speculative groups)
+    bool have_ed = false;            // ed_next below is errorD of the next sample
+    float ed_next = 0.0f;
+    bool dead = false;               // a hand-off timed out: stay on the checked path
+    int backoff = 0, skip = 0;       // after a failed group: run `skip` groups checked, then retry
+    int n_groups = 0, n_redone = 0;
+    if (warp == 0) {
+        ch.integ = st[0];
+        ch.ph = st[1];
+        ch.fi = st[2];
+        ch.fq = st[3];
+        ch.toff = toff0;
+        chain_load(ch, k);
+    }
+    __syncthreads();
+
+    for (int base = 0, g = 0; base < n; base += PLL_GROUP, g++) {
+        const int cnt = min(PLL_GROUP, n - base);
+        Chain ck;
+        // ---- group header (warp 0) ----
+        if (warp == 0) {
+            ck = ch;
+            const bool spec = regular && !dead && skip == 0 && ch.binade != FMRX_DISARMED;
+            if (lane == 0) {
+                s_flag[0] = spec;
+                s_grid[0] = ch.ulp;
+                s_grid[1] = ch.inv_ulp;
+                // phaseEst "of steps base-L .. base-1" for the first candidate tables
+                const double phd = (double)ch.ph;
+                for (int j = 1; j <= PLL_LOOKBACK; j++)
+                    s_ph[(base - j) & (PLL_TABLES - 1)] = make_int4(__double2loint(phd), __double2hiint(phd), base - j + 1, 0);
+            }
+        }
+        __syncthreads();
+        const bool spec = s_flag[0] != 0;
+        const double ulp = s_grid[0], inv_ulp = s_grid[1];
+
+        if (warp == 0) {
+            // ================= the chain =================
+            n_groups++;
+            bool good = spec;
+            if (spec) {
+                const unsigned binade = ch.binade;
+                float integ = ch.integ, ph = ch.ph;
+                float ed = ed_next;
+                if (!have_ed) {      // first group, or after a checked group: from the known trigArg
+                    const PllIn i0 = s_in[base & (PLL_RING - 1)];
+                    const Feedback f0 = make_feedback(K, ch.tad, i2d(i0.turn_hi, 0), i0.inv_x, nullptr, nullptr);
+                    ed = error_from_feedback(f0, i0.x, i0.xd, good);
+                }
+                // wait (bounded) for the first tables of the group; afterwards the candidate
+                // warps run ahead and a late table only clears `good`
+                for (int t = 0; t < PLL_LOOKBACK && t < cnt; t++) {
+                    const int want = base + t + 1;
+                    int spin = 0;
+                    for (;;) {
+                        const int z = ld_v4(&s_tab[(base + t) & (PLL_TABLES - 1)][0]).z;
+                        if (z == want || z == -want || ++spin >= PLL_SPIN_LIMIT)
+                            break;
+                    }
+                    if (spin >= PLL_SPIN_LIMIT) {
+                        dead = true;
+                        good = false;
+                        if (lane == 0)
+                            s_flag[1] = 1;
+                    }
+                }
+                int gi = 0;
+                double v = s_in[base & (PLL_RING - 1)].v;
+                // one step: loop filter, sum, grid index, table lookup.  No branches.
+                auto step = [&](int t) {
+                    const int u = base + t;
+                    const double v_next = s_in[(u + 1) & (PLL_RING - 1)].v;
+                    double phd;
+                    const double s = filter_step(k, ed, v, integ, ph, phd);           // :163-167
+                    // publish phaseEst(u) for a later candidate table: one 16-byte store
+                    if (lane == 0)
+                        st_v4(&s_ph[u & (PLL_TABLES - 1)], __double2loint(phd), __double2hiint(phd), u + 1, 0);
+                    gi = grid_index(grid_round(s, inv_ulp));
+                    // the candidate that IS trigArg(u) carries errorD of sample u+1 and proves it
+                    const int4 e = ld_v4(&s_tab[u & (PLL_TABLES - 1)][gi & 31]);
+                    ed = __int_as_float(e.x);
+                    good &= e.y == gi && e.z == u + 1;
+                    if (lane == 0)
+                        s_g[g & 1][t] = gi;
+                    v = v_next;
+                };
+                int t = 0;
+                if (good) {
+                    for (; t + 8 <= cnt; t += 8) {
+                        step(t);
+                        step(t + 1);
+                        step(t + 2);
+                        step(t + 3);
+                        step(t + 4);
+                        step(t + 5);
+                        step(t + 6);
+                        step(t + 7);
+                    }
+                    for (; t < cnt; t++)
+                        step(t);
+                }
+                if (good) {
+                    ch.integ = integ;
+                    ch.ph = ph;
+                    ch.toff = (float)min(t0 + base + cnt, 16777216);
+                    ch.tad = p_mul((double)gi, ulp);
+                    stale = true;
+                    have_ed = true;
+                    ed_next = ed;
+                    backoff = 0;
+                }
+            }
+            if (!good) {
+                if (spec) {
+                    n_redone++;
+                    backoff = min(backoff ? 2 * backoff : 1, 64);
+                    skip = backoff;
+                } else if (skip > 0) {
+                    skip--;
+                }
+                ch = ck;
+                if (stale) {         // bring the sincos leftovers up to date with ch.tad
+                    chain_refresh(ch);
+                    stale = false;
+                }
+                for (int t = 0; t < cnt; t++) {
+                    const float ta = chain_step(ch, k, K, s_in[(base + t) & (PLL_RING - 1)].x, nullptr);
+                    if (lane == 0)
+                        s_g[g & 1][t] = __float_as_int(ta);          // checked groups park the float itself
+                }
+                have_ed = false;
+            }
+            if (lane == 0) {
+                s_spec[g & 1] = good ? 1 : 0;
+                s_ulp_hist[g & 1] = ulp;
+            }
+        } else if (warp != PLL_IO_WARP) {
+            // ================= candidate tables: warp cand_id takes steps t = cand_id (mod 6) =================
+            if (spec) {
+                for (int t = cand_id; t < cnt; t += PLL_CAND_WARPS) {
+                    const int u = base + t;
+                    const double v = s_in[u & (PLL_RING - 1)].v;
+                    const PllIn nx = s_in[(u + 1) & (PLL_RING - 1)];     // the sample the result is for
+                    // phaseEst(u - PLL_LOOKBACK)
+                    int4 pr = ld_v4(&s_ph[(u - PLL_LOOKBACK) & (PLL_TABLES - 1)]);
+                    for (int spin = 0; pr.z != u - PLL_LOOKBACK + 1 && spin < PLL_SPIN_LIMIT; spin++)
+                        pr = ld_v4(&s_ph[(u - PLL_LOOKBACK) & (PLL_TABLES - 1)]);
+                    if (pr.z != u - PLL_LOOKBACK + 1) {
+                        s_flag[1] = 1;           // gave up: warp 0 will see missing tables and redo
+                        break;
+                    }
+                    // this lane's grid point: the one congruent to `lane` (mod 32) in [G_c-16, G_c+15]
+                    const int gc = grid_index(grid_round(p_add(v, i2d(pr.y, pr.x)), inv_ulp));
+                    const int gl = gc - 16 + ((lane - (gc - 16)) & 31);
+                    const double tad = p_mul((double)gl, ulp);                        // exact
+                    const Feedback f = make_feedback(K, tad, i2d(nx.turn_hi, 0), nx.inv_x, nullptr, nullptr);
+                    // the float grid of the binade is only right strictly inside it
+                    const int ag = gl < 0 ? -gl : gl;
+                    bool ok = ag > (1 << 23) && ag < (1 << 24);
+                    const float ed = error_from_feedback(f, nx.x, nx.xd, ok);         // :159-161 of sample u+1
+                    st_v4(&s_tab[u & (PLL_TABLES - 1)][lane], __float_as_int(ed), gl, ok ? u + 1 : -(u + 1), 0);
+                }
+            }
+        } else {
+            // ================= I/O =================
+            prepare(base + 2 * PLL_GROUP);
+            if (g > 0) {                     // previous group: always complete
+                const int pb = base - PLL_GROUP;
+                for (int j = lane; j < PLL_GROUP; j += 32)
+                    tr[pb + j] = s_spec[(g - 1) & 1] ? __double2float_rn(p_mul((double)s_g[(g - 1) & 1][j], s_ulp_hist[(g - 1) & 1]))
+                                                     : __int_as_float(s_g[(g - 1) & 1][j]);
+            }
+        }
+        __syncthreads();
+    }
+    // the last group's trigArg
+    if (warp == PLL_IO_WARP && n > 0) {
+        const int g = (n - 1) / PLL_GROUP, pb = g * PLL_GROUP;
+        for (int j = lane; pb + j < n && j < PLL_GROUP; j += 32)
+            tr[pb + j] = s_spec[g & 1] ? __double2float_rn(p_mul((double)s_g[g & 1][j], s_ulp_hist[g & 1]))
+                                       : __int_as_float(s_g[g & 1][j]);
+    }
+    if (warp == 0 && lane == 0) {
         if (stale)
             chain_refresh(ch);
         float fi, fq;
@@ -446,7 +560,7 @@ __global__ void __launch_bounds__(32) k_pll(const PllArgs a)
         st[3] = fq;
         st[5] = ch.toff;
         st[6] = (float)n_groups;     // diagnostics of the last launch
-        st[7] = (float)n_redone;
+        st[7] = s_flag[1] ? -1.0f : (float)n_redone;
         if (n > 0)
             st[4] = nco_from_trig(__double2float_rn(ch.tad), a.prm.scale, a.prm.adjust);   // :173
     }
@@ -456,7 +570,7 @@ cudaError_t launch_pll(const PllArgs &a_in, int n_captures, cudaStream_t s)
 {
     PllArgs a = a_in;
     a.kconst = pllcore::trig_constants();
-    k_pll<<<n_captures, 32, 0, s>>>(a);
+    k_pll<<<n_captures, PLL_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
 

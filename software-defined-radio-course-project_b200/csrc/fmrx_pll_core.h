@@ -345,11 +345,9 @@ FMRX_HD Feedback make_feedback(const TrigK &K, double tad, double turn, double i
     return f;
 }
 
-// atan2 + loop filter of one sample (:159-167): updates integ, ph and returns
-// s = w*trigOffset + phaseEst in double (the value the reference then stores to a
-// float).  `ok` is cleared if a guard of the atan2 shortcut fails.
-FMRX_HD double step_front(const Consts &k, const Feedback &f, float x, double xd, double v, float &integ,
-                          float &ph, double &phd, bool &ok)
+// The phase-detector output errorD = fl32(atan2(eQ, eI)) of one sample (:159-161) from
+// the feedback prepared for it.  `ok` is cleared if a guard of the shortcut fails.
+FMRX_HD float error_from_feedback(const Feedback &f, float x, double xd, bool &ok)
 {
     const float ei = p_fmulf(x, f.cf);                               // :159 (up to the quadrant)
     const float eq = p_fmulf(x, -f.sf);                              // :160
@@ -360,12 +358,26 @@ FMRX_HD double step_front(const Consts &k, const Feedback &f, float x, double xd
     const double dotc = p_fma(-f.snx, tq, p_mul(f.csx, ti));   // radial part (second order)
     const double a1 = p_fma(-f.snx, ti, p_add(f.phi, -m1));    // phi + cross
     const double alpha = p_fma(-cross, dotc, a1);              // phi + cross*(1 - dotc)
-    const float ed = p_d2f(-alpha);                                  // :161
     ok = ok && fabs(cross) < 0x1p-20 && fabs(dotc) < 0x1p-20 && fabs(f.phi) < 3.125;
+    return p_d2f(-alpha);                                            // :161
+}
+
+// The loop filter (:163-164) and the double sum the reference then stores to a float
+// (:167): updates integ, ph; returns s = w*trigOffset + phaseEst.
+FMRX_HD double filter_step(const Consts &k, float ed, double v, float &integ, float &ph, double &phd)
+{
     integ = p_faddf(integ, p_fmulf(k.ki, ed));                       // :163
     ph = p_faddf(ph, p_faddf(p_fmulf(k.kp, ed), integ));             // :164
     phd = (double)ph;
     return p_add(v, phd);                                            // :167 in double
+}
+
+// atan2 + loop filter of one sample (:159-167).
+FMRX_HD double step_front(const Consts &k, const Feedback &f, float x, double xd, double v, float &integ,
+                          float &ph, double &phd, bool &ok)
+{
+    const float ed = error_from_feedback(f, x, xd, ok);
+    return filter_step(k, ed, v, integ, ph, phd);
 }
 
 // rint(s/ulp) as a double holding an integer plus the magic constant: its low word is
