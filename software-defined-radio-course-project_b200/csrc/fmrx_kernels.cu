@@ -455,15 +455,10 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 };
                 int t = 0;
                 if (good) {
-                    for (; t + 8 <= cnt; t += 8) {
-                        step(t);
-                        step(t + 1);
-                        step(t + 2);
-                        step(t + 3);
-                        step(t + 4);
-                        step(t + 5);
-                        step(t + 6);
-                        step(t + 7);
+                    for (; t + 16 <= cnt; t += 16) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                            step(t + j);
                     }
                     for (; t < cnt; t++)
                         step(t);
@@ -492,10 +487,32 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     chain_refresh(ch);
                     stale = false;
                 }
-                for (int t = 0; t < cnt; t++) {
-                    const float ta = chain_step(ch, k, K, s_in[(base + t) & (PLL_RING - 1)].x, nullptr);
-                    if (lane == 0)
-                        s_g[g & 1][t] = __float_as_int(ta);          // checked groups park the float itself
+                // second line: the single-warp speculative step (sequential make_feedback on the
+                // chain, ~300 cycles per step) over the whole group from a checkpoint ...
+                const Chain ck2 = ch;
+                bool ok2 = regular && ch.binade != FMRX_DISARMED;
+                if (ok2) {
+                    for (int t = 0; t < cnt; t++) {
+                        const PllIn i = s_in[(base + t) & (PLL_RING - 1)];
+                        StepIn in;
+                        in.x = i.x;
+                        in.xd = i.xd;
+                        in.inv_x = i.inv_x;
+                        in.turn = i2d(i.turn_hi, 0);
+                        in.v = i.v;
+                        ok2 &= chain_step_spec(ch, k, K, in);
+                        if (lane == 0)
+                            s_g[g & 1][t] = __float_as_int(__double2float_rn(ch.tad));
+                    }
+                }
+                // ... and if one of ITS guards failed too, the checked/generic step, one by one
+                if (!ok2) {
+                    ch = ck2;
+                    for (int t = 0; t < cnt; t++) {
+                        const float ta = chain_step(ch, k, K, s_in[(base + t) & (PLL_RING - 1)].x, nullptr);
+                        if (lane == 0)
+                            s_g[g & 1][t] = __float_as_int(ta);          // checked groups park the float itself
+                    }
                 }
                 have_ed = false;
             }
