@@ -227,14 +227,14 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 // ============================================================================
 // The recurrence is one dependent chain per capture, so its latency bounds the
 // throughput of the whole receive chain; fmrx_pll_core.h holds the low-latency
-// formulation of one step and the measurements behind it.  One CTA of eight warps per
+// formulation of one step and the measurements behind it.  One CTA of twelve warps per
 // capture, every warp SIMT-uniform or one-lane-per-item:
 //
 //   warp 0  the chain, reduced to what is irreducibly sequential: the four float
 //           operations of the loop filter, the conversion of phaseEst to double, the sum
 //           s = w*trigOffset + phaseEst, its grid index G = rint(s/ulp) -- and then a
 //           TABLE LOOKUP of the next phase-detector output.  About 95 dependent cycles.
-//   warps 1-3, 5-7  value speculation.  trigArg(u) = fl32(s) lives on the float grid of
+//   warps 2,3,5-7,9-11  value speculation.  trigArg(u) = fl32(s) lives on the float grid of
 //           its binade (spacing 2^-7 .. 0.5 rad after the first second) and a few
 //           loop-filter updates move phaseEst by far less than that, so trigArg(u) is one
 //           of a handful of grid points around rint((w*trigOffset(u) + phaseEst(u-L))/ulp).
@@ -245,7 +245,7 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 //           the atan2 shortcut -- i.e. errorD(u+1) = fl32(atan2(eQ, eI)) of the NEXT sample
 //           for each candidate (SIMT: the instructions of a single evaluation).  The entry
 //           warp 0 picks is bit for bit what the sequential formulation computes.
-//   warp 4  I/O.  One lane per sample: the coalesced pilot load, (double)x, the IEEE
+//   warp 1  I/O.  One lane per sample: the coalesced pilot load, (double)x, the IEEE
 //           reciprocal 1/x, the half-turn flag and w*trigOffset for the group after next
 //           into a 4-group ring in shared memory; and the coalesced store of the previous
 //           group's trigArg.
@@ -262,14 +262,14 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 // Only trigArg leaves the chain; the NCO output cos(trigArg*scale+adjust) is evaluated
 // in K4.
 
-constexpr int PLL_WARPS = 8;
+constexpr int PLL_WARPS = 12;
 constexpr int PLL_THREADS = 32 * PLL_WARPS;
-constexpr int PLL_CAND_WARPS = 6;        // warps 1,2,3,5,6,7
-constexpr int PLL_IO_WARP = 4;           // shares a scheduler with warp 0 but is idle most of the time
-constexpr int PLL_GROUP = 128;           // steps between checkpoints / barriers
+constexpr int PLL_CAND_WARPS = 8;        // warps 2,3,5,6,7,9,10,11: never on warp 0's scheduler
+constexpr int PLL_IO_WARP = 1;           // warps 4 and 8 (warp 0's scheduler) only take part in the barriers
+constexpr int PLL_GROUP = 512;           // steps between checkpoints / barriers
 constexpr int PLL_RING = 4 * PLL_GROUP;  // per-sample input ring: 4 groups
-constexpr int PLL_TABLES = 16;           // candidate tables / phaseEst records in flight
-constexpr int PLL_LOOKBACK = 8;          // candidates for trigArg(u) are centred on phaseEst(u - PLL_LOOKBACK)
+constexpr int PLL_TABLES = 32;           // candidate tables / phaseEst records in flight
+constexpr int PLL_LOOKBACK = 12;         // candidates for trigArg(u) are centred on phaseEst(u - PLL_LOOKBACK)
 constexpr int PLL_SPIN_LIMIT = 1 << 16;  // bounded polling (~1 ms): a bug must not hang the GPU
 
 struct __align__(16) PllIn {             // off-chain inputs of one sample
@@ -278,6 +278,9 @@ struct __align__(16) PllIn {             // off-chain inputs of one sample
     double xd;                           // (double)x
     double inv_x;                        // 1/(double)x, IEEE divide
     double v;                            // w * trigOffset after this step (:166-167)
+    int vi;                              // rint(v/ulp) for the binade the slot was prepared in ...
+    float vr;                            // ... and fl32(v/ulp - vi), |vr| <= 0.5
+    int pad[2];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -306,13 +309,15 @@ __device__ __forceinline__ double i2d(int hi, int lo) { return __hiloint2double(
 __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
 {
     using namespace pllcore;
-    __shared__ PllIn s_in[PLL_RING];
+    extern __shared__ __align__(16) unsigned char pll_dyn_smem[];
+    PllIn *s_in = reinterpret_cast<PllIn *>(pll_dyn_smem);      // [PLL_RING]
     __shared__ int4 s_ph[PLL_TABLES];                 // {phaseEst lo, hi, seq, -}: published by warp 0
-    // candidate tables, indexed by (step & 15, grid index & 31): {errorD of the next sample, grid
-    // index, step+1 (negated if a guard failed), -}; one self-validating 16-byte record per lane
+    // candidate tables, indexed by (step & 15, grid index & 31): {Kp*errorD, Ki*errorD of the next
+    // sample, grid index, step+1 (negated if a guard failed)}; one self-validating 16-byte record per lane
     __shared__ int4 s_tab[PLL_TABLES][32];
     __shared__ int s_g[2][PLL_GROUP];                 // grid index of each trigArg of the group, double-buffered
     __shared__ double s_grid[2];                      // ulp, 1/ulp of the current group
+    __shared__ double s_prep_ulp[4];                  // ulp the ring slots of each group were prepared with
     __shared__ double s_ulp_hist[2];                  // ulp the parked grid indices of a group refer to
     __shared__ int s_spec[2];                         // 1: s_g holds grid indices, 0: float bit patterns
     __shared__ int s_flag[4];                         // [0] group runs speculatively, [1] error
@@ -334,8 +339,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     const float toff0 = st[5];
     const bool regular = toff_is_regular(toff0);
     const int t0 = regular ? (int)toff0 : 0;
-    // candidate warps: 1,2,3,5,6,7 -> 0..5
-    const int cand_id = (warp < PLL_IO_WARP) ? warp - 1 : warp - 2;
+    // candidate warps: 2,3,5,6,7,9,10,11 -> 0..7
+    const int cand_id = warp - 2 - (warp >> 2);
 
     // I/O warp: one lane per sample, off-chain inputs of the samples of a group into the ring
     auto prepare = [&](int base) {
@@ -349,29 +354,31 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             in.inv_x = 1.0 / in.xd;                                      // IEEE divide
             const float toff = (float)min(t0 + u + 1, 16777216);         // exact: <= 2^24
             in.v = __dmul_rn(k.w, (double)toff);
+            // v on the float grid of the current binade: integer part and remainder
+            const double qv = grid_round(in.v, s_grid[1]);
+            in.vi = grid_index(qv);
+            in.vr = __double2float_rn(__fma_rn(in.v, s_grid[1], -p_add(qv, -FMRX_RINT_MAGIC)));
+            in.pad[0] = in.pad[1] = 0;
             s_in[u & (PLL_RING - 1)] = in;
         }
+        if (lane == 0)
+            s_prep_ulp[(base / PLL_GROUP) & 3] = s_grid[0];
     };
 
     if (threadIdx.x < PLL_TABLES)
         s_ph[threadIdx.x] = make_int4(0, 0, (int)0x80000000, 0);
     for (int i = threadIdx.x; i < PLL_TABLES * 32; i += PLL_THREADS)
-        s_tab[i >> 5][i & 31] = make_int4(0, 0, (int)0x80000000, 0);
+        s_tab[i >> 5][i & 31] = make_int4(0, 0, 0, (int)0x80000000);
     if (threadIdx.x == 0)
         s_flag[1] = 0;
-    if (warp == PLL_IO_WARP) {
-        prepare(0);
-        prepare(PLL_GROUP);
-    }
-
     // warp 0 owns the recurrence state
     Chain ch;
     bool stale = false;              // ch's sincos leftovers lag behind ch.tad (after speculative groups)
-    bool have_ed = false;            // ed_next below is errorD of the next sample
-    float ed_next = 0.0f;
+    bool have_ed = false;            // kpe_next/kie_next below belong to the next sample
+    float kpe_next = 0.0f, kie_next = 0.0f;
     bool dead = false;               // a hand-off timed out: stay on the checked path
     int backoff = 0, skip = 0;       // after a failed group: run `skip` groups checked, then retry
-    int n_groups = 0, n_redone = 0;
+    int n_groups = 0, n_redone = 0, n_tab = 0, n_frac = 0, n_tt = 0;
     if (warp == 0) {
         ch.integ = st[0];
         ch.ph = st[1];
@@ -379,6 +386,15 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         ch.fq = st[3];
         ch.toff = toff0;
         chain_load(ch, k);
+        if (lane == 0) {
+            s_grid[0] = ch.ulp;
+            s_grid[1] = ch.inv_ulp;
+        }
+    }
+    __syncthreads();
+    if (warp == PLL_IO_WARP) {
+        prepare(0);
+        prepare(PLL_GROUP);
     }
     __syncthreads();
 
@@ -388,7 +404,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         // ---- group header (warp 0) ----
         if (warp == 0) {
             ck = ch;
-            const bool spec = regular && !dead && skip == 0 && ch.binade != FMRX_DISARMED;
+            const bool spec = regular && !dead && skip == 0 && ch.binade != FMRX_DISARMED &&
+                              s_prep_ulp[g & 3] == ch.ulp;
             if (lane == 0) {
                 s_flag[0] = spec;
                 s_grid[0] = ch.ulp;
@@ -408,21 +425,33 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             n_groups++;
             bool good = spec;
             if (spec) {
-                const unsigned binade = ch.binade;
                 float integ = ch.integ, ph = ch.ph;
-                float ed = ed_next;
+                float kpe = kpe_next, kie = kie_next;        // Kp*errorD, Ki*errorD of the sample about to run
                 if (!have_ed) {      // first group, or after a checked group: from the known trigArg
                     const PllIn i0 = s_in[base & (PLL_RING - 1)];
                     const Feedback f0 = make_feedback(K, ch.tad, i2d(i0.turn_hi, 0), i0.inv_x, nullptr, nullptr);
-                    ed = error_from_feedback(f0, i0.x, i0.xd, good);
+                    const float ed = error_from_feedback(f0, i0.x, i0.xd, good);
+                    kpe = p_fmulf(k.kp, ed);
+                    kie = p_fmulf(k.ki, ed);
                 }
+                // The grid index of trigArg(u) = fl32(v(u) + phaseEst) without leaving the FP32
+                // pipe: with v(u)/ulp = vi + vr (integer + remainder, prepared per sample) and
+                // phaseEst/ulp = pi + t (pi = rint at the group start, so |t| stays small),
+                //     G = vi + pi + rint(t + vr),   t = fma(phaseEst, 1/ulp, -pi)  (one rounding)
+                // All roundings together stay below 2^-20 of a grid step while |t| < 8 (and the
+                // reference's own double rounding of v + phaseEst moves the sum by < 2^-29), so a
+                // sum farther than 2^-18 from a tie rounds the same way; closer ones (4e-6 of the
+                // steps) fail the guard and the group is redone the exact way.
+                const float inv_ulp_f = (float)inv_ulp;                          // a power of two
+                const float pi_f = rintf(p_fmulf(ph, inv_ulp_f));
+                const int cu_base = (int)pi_f - 0x4B400000;
                 // wait (bounded) for the first tables of the group; afterwards the candidate
                 // warps run ahead and a late table only clears `good`
                 for (int t = 0; t < PLL_LOOKBACK && t < cnt; t++) {
                     const int want = base + t + 1;
                     int spin = 0;
                     for (;;) {
-                        const int z = ld_v4(&s_tab[(base + t) & (PLL_TABLES - 1)][0]).z;
+                        const int z = ld_v4(&s_tab[(base + t) & (PLL_TABLES - 1)][0]).w;
                         if (z == want || z == -want || ++spin >= PLL_SPIN_LIMIT)
                             break;
                     }
@@ -433,25 +462,36 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                             s_flag[1] = 1;
                     }
                 }
+                bool dbg_tab = false, dbg_frac = false, dbg_tt = false;
                 int gi = 0;
-                double v = s_in[base & (PLL_RING - 1)].v;
-                // one step: loop filter, sum, grid index, table lookup.  No branches.
+                int2 vg = *reinterpret_cast<const int2 *>(&s_in[base & (PLL_RING - 1)].vi);     // {vi, vr}
+                // one step: loop filter, grid index, table lookup.  No branches, no FP64 on the chain.
                 auto step = [&](int t) {
                     const int u = base + t;
-                    const double v_next = s_in[(u + 1) & (PLL_RING - 1)].v;
-                    double phd;
-                    const double s = filter_step(k, ed, v, integ, ph, phd);           // :163-167
-                    // publish phaseEst(u) for a later candidate table: one 16-byte store
-                    if (lane == 0)
-                        st_v4(&s_ph[u & (PLL_TABLES - 1)], __double2loint(phd), __double2hiint(phd), u + 1, 0);
-                    gi = grid_index(grid_round(s, inv_ulp));
-                    // the candidate that IS trigArg(u) carries errorD of sample u+1 and proves it
+                    const int2 vg_next = *reinterpret_cast<const int2 *>(&s_in[(u + 1) & (PLL_RING - 1)].vi);
+                    integ = p_faddf(integ, kie);                                  // :163
+                    ph = p_faddf(ph, p_faddf(kpe, integ));                       // :164
+                    const float tt = __fmaf_rn(ph, inv_ulp_f, -pi_f);
+                    const float z = p_faddf(tt, __int_as_float(vg.y));
+                    const float zm = p_faddf(z, 12582912.0f);                     // 1.5 * 2^23: rint in the low bits
+                    gi = __float_as_int(zm) + (vg.x + cu_base);                   // :166-167 as a grid index
+                    // the candidate that IS trigArg(u) carries Kp*errorD, Ki*errorD of sample u+1 and proves it
                     const int4 e = ld_v4(&s_tab[u & (PLL_TABLES - 1)][gi & 31]);
-                    ed = __int_as_float(e.x);
-                    good &= e.y == gi && e.z == u + 1;
-                    if (lane == 0)
+                    kpe = __int_as_float(e.x);
+                    kie = __int_as_float(e.y);
+                    const float frac = p_faddf(z, -p_faddf(zm, -12582912.0f));
+                    good &= e.z == gi && e.w == u + 1 && fabsf(frac) < 0.499996185302734375f && fabsf(tt) < 8.0f;
+                    dbg_tab |= !(e.z == gi && e.w == u + 1);
+                    dbg_frac |= !(fabsf(frac) < 0.499996185302734375f);
+                    dbg_tt |= !(fabsf(tt) < 8.0f);
+                    // off the chain: publish phaseEst(u) for a later candidate table (one 16-byte
+                    // store) and park the grid index for the I/O warp
+                    if (lane == 0) {
+                        const double phd = (double)ph;
+                        st_v4(&s_ph[u & (PLL_TABLES - 1)], __double2loint(phd), __double2hiint(phd), u + 1, 0);
                         s_g[g & 1][t] = gi;
-                    v = v_next;
+                    }
+                    vg = vg_next;
                 };
                 int t = 0;
                 if (good) {
@@ -463,6 +503,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     for (; t < cnt; t++)
                         step(t);
                 }
+                n_tab += dbg_tab; n_frac += dbg_frac; n_tt += dbg_tt;
                 if (good) {
                     ch.integ = integ;
                     ch.ph = ph;
@@ -470,7 +511,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     ch.tad = p_mul((double)gi, ulp);
                     stale = true;
                     have_ed = true;
-                    ed_next = ed;
+                    kpe_next = kpe;
+                    kie_next = kie;
                     backoff = 0;
                 }
             }
@@ -520,8 +562,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 s_spec[g & 1] = good ? 1 : 0;
                 s_ulp_hist[g & 1] = ulp;
             }
-        } else if (warp != PLL_IO_WARP) {
-            // ================= candidate tables: warp cand_id takes steps t = cand_id (mod 6) =================
+        } else if ((warp & 3) != 0 && warp != PLL_IO_WARP) {
+            // ================= candidate tables: warp cand_id takes steps t = cand_id (mod PLL_CAND_WARPS) =================
             if (spec) {
                 for (int t = cand_id; t < cnt; t += PLL_CAND_WARPS) {
                     const int u = base + t;
@@ -544,10 +586,11 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const int ag = gl < 0 ? -gl : gl;
                     bool ok = ag > (1 << 23) && ag < (1 << 24);
                     const float ed = error_from_feedback(f, nx.x, nx.xd, ok);         // :159-161 of sample u+1
-                    st_v4(&s_tab[u & (PLL_TABLES - 1)][lane], __float_as_int(ed), gl, ok ? u + 1 : -(u + 1), 0);
+                    st_v4(&s_tab[u & (PLL_TABLES - 1)][lane], __float_as_int(p_fmulf(k.kp, ed)), __float_as_int(p_fmulf(k.ki, ed)), gl,
+                          ok ? u + 1 : -(u + 1));
                 }
             }
-        } else {
+        } else if (warp == PLL_IO_WARP) {
             // ================= I/O =================
             prepare(base + 2 * PLL_GROUP);
             if (g > 0) {                     // previous group: always complete
@@ -576,8 +619,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         st[2] = fi;
         st[3] = fq;
         st[5] = ch.toff;
-        st[6] = (float)n_groups;     // diagnostics of the last launch
-        st[7] = s_flag[1] ? -1.0f : (float)n_redone;
+        st[6] = (float)(n_groups + 1000 * n_tab);     // diagnostics of the last launch
+        st[7] = s_flag[1] ? -1.0f : (float)(n_redone + 1000 * n_frac + 1000000 * n_tt);
         if (n > 0)
             st[4] = nco_from_trig(__double2float_rn(ch.tad), a.prm.scale, a.prm.adjust);   // :173
     }
@@ -587,7 +630,15 @@ cudaError_t launch_pll(const PllArgs &a_in, int n_captures, cudaStream_t s)
 {
     PllArgs a = a_in;
     a.kconst = pllcore::trig_constants();
-    k_pll<<<n_captures, PLL_THREADS, 0, s>>>(a);
+    static bool configured = false;
+    const size_t dyn = sizeof(PllIn) * PLL_RING;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_pll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess)
+            return e;
+        configured = true;
+    }
+    k_pll<<<n_captures, PLL_THREADS, dyn, s>>>(a);
     return cudaGetLastError();
 }
 
