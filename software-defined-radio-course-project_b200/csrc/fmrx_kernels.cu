@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     // candidate tables, indexed by (step & 15, grid index & 31): {Kp*errorD, Ki*errorD of the next
     // sample, grid index, step+1 (negated if a guard failed)}; one self-validating 16-byte record per lane
     __shared__ int4 s_tab[PLL_TABLES][32];
-    __shared__ int s_g[2][PLL_GROUP];                 // grid index of each trigArg of the group, double-buffered
+    __shared__ __align__(16) int s_g[2][PLL_GROUP];                 // grid index of each trigArg of the group, double-buffered
     __shared__ double s_grid[2];                      // ulp, 1/ulp of the current group
     __shared__ double s_prep_ulp[4];                  // ulp the ring slots of each group were prepared with
     __shared__ double s_ulp_hist[2];                  // ulp the parked grid indices of a group refer to
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     float kpe_next = 0.0f, kie_next = 0.0f;
     bool dead = false;               // a hand-off timed out: stay on the checked path
     int backoff = 0, skip = 0;       // after a failed group: run `skip` groups checked, then retry
-    int n_groups = 0, n_redone = 0, n_tab = 0, n_frac = 0, n_tt = 0;
+    int n_groups = 0, n_redone = 0, n_tab = 0, n_frac = 0;
     if (warp == 0) {
         ch.integ = st[0];
         ch.ph = st[1];
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 s_grid[1] = ch.inv_ulp;
                 // phaseEst "of steps base-L .. base-1" for the first candidate tables
                 const double phd = (double)ch.ph;
-                for (int j = 1; j <= PLL_LOOKBACK; j++)
+                for (int j = 1; j <= PLL_LOOKBACK + 3; j++)
                     s_ph[(base - j) & (PLL_TABLES - 1)] = make_int4(__double2loint(phd), __double2hiint(phd), base - j + 1, 0);
             }
         }
@@ -436,15 +436,24 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 }
                 // The grid index of trigArg(u) = fl32(v(u) + phaseEst) without leaving the FP32
                 // pipe: with v(u)/ulp = vi + vr (integer + remainder, prepared per sample) and
-                // phaseEst/ulp = pi + t (pi = rint at the group start, so |t| stays small),
+                // phaseEst/ulp = pi + t (pi = rint, at the group start, so |t| stays small),
                 //     G = vi + pi + rint(t + vr),   t = fma(phaseEst, 1/ulp, -pi)  (one rounding)
-                // All roundings together stay below 2^-20 of a grid step while |t| < 8 (and the
-                // reference's own double rounding of v + phaseEst moves the sum by < 2^-29), so a
-                // sum farther than 2^-18 from a tie rounds the same way; closer ones (4e-6 of the
-                // steps) fail the guard and the group is redone the exact way.
+                // The roundings of t, of t + vr and of vr together stay below 2^-21.5 * max(|t|, 1) of
+                // a grid step (and the reference's own double rounding of v + phaseEst moves the sum
+                // by < 2^-29), so a sum farther than 2^-20 * max(|t|, 4) from a tie rounds the same
+                // way; closer ones (a few per million steps) fail the guard and the group is redone
+                // the exact way.
                 const float inv_ulp_f = (float)inv_ulp;                          // a power of two
-                const float pi_f = rintf(p_fmulf(ph, inv_ulp_f));
-                const int cu_base = (int)pi_f - 0x4B400000;
+                float pi_f = 0.0f;
+                int cu_base = 0;
+                // centre pi on the current phaseEst
+                auto recentre = [&]() {
+                    const float pm = p_faddf(p_fmulf(ph, inv_ulp_f), 12582912.0f);   // rint via 1.5*2^23
+                    pi_f = p_faddf(pm, -12582912.0f);
+                    cu_base = __float_as_int(pm) - 0x4B400000 - 0x4B400000;
+                    good &= fabsf(pi_f) < 2097152.0f;                              // |phaseEst/ulp| < 2^21
+                };
+                recentre();
                 // wait (bounded) for the first tables of the group; afterwards the candidate
                 // warps run ahead and a late table only clears `good`
                 for (int t = 0; t < PLL_LOOKBACK && t < cnt; t++) {
@@ -462,13 +471,12 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                             s_flag[1] = 1;
                     }
                 }
-                bool dbg_tab = false, dbg_frac = false, dbg_tt = false;
+                int bad = 0;                 // OR of (table key ^ expected key) over the steps
+                float worst = 0.0f;          // max of |frac| + margin over the steps; must stay < 0.5
                 int gi = 0;
-                int2 vg = *reinterpret_cast<const int2 *>(&s_in[base & (PLL_RING - 1)].vi);     // {vi, vr}
                 // one step: loop filter, grid index, table lookup.  No branches, no FP64 on the chain.
-                auto step = [&](int t) {
-                    const int u = base + t;
-                    const int2 vg_next = *reinterpret_cast<const int2 *>(&s_in[(u + 1) & (PLL_RING - 1)].vi);
+                // in_a = shared address of this sample's ring slot, tab_a = of its table row.
+                auto step = [&](int u, unsigned in_a, unsigned tab_a, int2 vg, bool publish) {
                     integ = p_faddf(integ, kie);                                  // :163
                     ph = p_faddf(ph, p_faddf(kpe, integ));                       // :164
                     const float tt = __fmaf_rn(ph, inv_ulp_f, -pi_f);
@@ -476,34 +484,68 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const float zm = p_faddf(z, 12582912.0f);                     // 1.5 * 2^23: rint in the low bits
                     gi = __float_as_int(zm) + (vg.x + cu_base);                   // :166-167 as a grid index
                     // the candidate that IS trigArg(u) carries Kp*errorD, Ki*errorD of sample u+1 and proves it
-                    const int4 e = ld_v4(&s_tab[u & (PLL_TABLES - 1)][gi & 31]);
+                    int4 e;
+                    asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                                 : "r"(((gi << 4) & 0x1f0) | tab_a)
+                                 : "memory");
                     kpe = __int_as_float(e.x);
                     kie = __int_as_float(e.y);
+                    bad |= (e.z ^ gi) | (e.w ^ (u + 1));
+                    // rounding budget: < 2^-21.5 * max(|t|, 1) of a grid step; margin 2^-20 * max(|t|, 4)
                     const float frac = p_faddf(z, -p_faddf(zm, -12582912.0f));
-                    good &= e.z == gi && e.w == u + 1 && fabsf(frac) < 0.499996185302734375f && fabsf(tt) < 8.0f;
-                    dbg_tab |= !(e.z == gi && e.w == u + 1);
-                    dbg_frac |= !(fabsf(frac) < 0.499996185302734375f);
-                    dbg_tt |= !(fabsf(tt) < 8.0f);
-                    // off the chain: publish phaseEst(u) for a later candidate table (one 16-byte
-                    // store) and park the grid index for the I/O warp
-                    if (lane == 0) {
+                    worst = fmaxf(worst, __fmaf_rn(fmaxf(fabsf(tt), 4.0f), 0x1p-20f, fabsf(frac)));
+                    // off the chain, every 4th step: publish phaseEst(u) for later candidate tables
+                    if (publish && lane == 0) {
                         const double phd = (double)ph;
                         st_v4(&s_ph[u & (PLL_TABLES - 1)], __double2loint(phd), __double2hiint(phd), u + 1, 0);
-                        s_g[g & 1][t] = gi;
                     }
-                    vg = vg_next;
+                    (void)in_a;
                 };
+                auto load_vg = [&](unsigned addr) {
+                    int2 v;
+                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+                    return v;
+                };
+                const unsigned in_base = smem_u32(&s_in[0]) + 32u;               // offset of {vi, vr} in a slot
+                const unsigned tab_base = smem_u32(&s_tab[0][0]);
                 int t = 0;
                 if (good) {
+                    int2 vg0 = load_vg(in_base + (unsigned)(base & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
                     for (; t + 16 <= cnt; t += 16) {
+                        const int u0 = base + t;
+                        // neither the ring nor the table wraps inside a block of 16 (both sizes are
+                        // multiples of 16 and u0 is one): addresses are base + constant
+                        const unsigned in_a0 = in_base + (unsigned)(u0 & (PLL_RING - 1)) * (unsigned)sizeof(PllIn);
+                        const unsigned tab_a0 = tab_base + (unsigned)(u0 & (PLL_TABLES - 1)) * 512u;
+                        const int2 vg_next_block =
+                            load_vg(in_base + (unsigned)((u0 + 16) & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
+                        int gis[16];
+                        int2 vg = vg0;
 #pragma unroll
-                        for (int j = 0; j < 16; j++)
-                            step(t + j);
+                        for (int j = 0; j < 16; j++) {
+                            const int2 vg_n = (j < 15) ? load_vg(in_a0 + (unsigned)(j + 1) * (unsigned)sizeof(PllIn)) : vg_next_block;
+                            step(u0 + j, 0u, tab_a0 + (unsigned)j * 512u, vg, (j & 3) == 0);
+                            gis[j] = gi;
+                            vg = vg_n;
+                        }
+                        vg0 = vg_next_block;
+                        if (lane == 0) {     // park the 16 grid indices for the I/O warp
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                *reinterpret_cast<int4 *>(&s_g[g & 1][t + j]) = make_int4(gis[j], gis[j + 1], gis[j + 2], gis[j + 3]);
+                        }
                     }
-                    for (; t < cnt; t++)
-                        step(t);
+                    for (; t < cnt; t++) {   // tail of the last group of a launch
+                        const int u = base + t;
+                        const int2 vg = load_vg(in_base + (unsigned)(u & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
+                        step(u, 0u, tab_base + (unsigned)(u & (PLL_TABLES - 1)) * 512u, vg, (u & 3) == 0);
+                        if (lane == 0)
+                            s_g[g & 1][t] = gi;
+                    }
+                    good = good && bad == 0 && worst < 0.5f;
                 }
-                n_tab += dbg_tab; n_frac += dbg_frac; n_tt += dbg_tt;
+                n_tab += (bad != 0); n_frac += !(worst < 0.5f);
                 if (good) {
                     ch.integ = integ;
                     ch.ph = ph;
@@ -569,11 +611,12 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const int u = base + t;
                     const double v = s_in[u & (PLL_RING - 1)].v;
                     const PllIn nx = s_in[(u + 1) & (PLL_RING - 1)];     // the sample the result is for
-                    // phaseEst(u - PLL_LOOKBACK)
-                    int4 pr = ld_v4(&s_ph[(u - PLL_LOOKBACK) & (PLL_TABLES - 1)]);
-                    for (int spin = 0; pr.z != u - PLL_LOOKBACK + 1 && spin < PLL_SPIN_LIMIT; spin++)
-                        pr = ld_v4(&s_ph[(u - PLL_LOOKBACK) & (PLL_TABLES - 1)]);
-                    if (pr.z != u - PLL_LOOKBACK + 1) {
+                    // phaseEst of the latest published step at or before u - PLL_LOOKBACK (every 4th is)
+                    const int ur = (u - PLL_LOOKBACK) & ~3;
+                    int4 pr = ld_v4(&s_ph[ur & (PLL_TABLES - 1)]);
+                    for (int spin = 0; pr.z != ur + 1 && spin < PLL_SPIN_LIMIT; spin++)
+                        pr = ld_v4(&s_ph[ur & (PLL_TABLES - 1)]);
+                    if (pr.z != ur + 1) {
                         s_flag[1] = 1;           // gave up: warp 0 will see missing tables and redo
                         break;
                     }
@@ -620,7 +663,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         st[3] = fq;
         st[5] = ch.toff;
         st[6] = (float)(n_groups + 1000 * n_tab);     // diagnostics of the last launch
-        st[7] = s_flag[1] ? -1.0f : (float)(n_redone + 1000 * n_frac + 1000000 * n_tt);
+        st[7] = s_flag[1] ? -1.0f : (float)(n_redone + 1000 * n_frac);
         if (n > 0)
             st[4] = nco_from_trig(__double2float_rn(ch.tad), a.prm.scale, a.prm.adjust);   // :173
     }
