@@ -31,6 +31,15 @@ __device__ __forceinline__ float unpack_u8(uint32_t v)
     return fmul(fsub((float)v, 128.0f), 0.0078125f);
 }
 
+// The same value from byte K of a packed word without an integer->float conversion:
+// 0x47800000 | b is the float 65536 + b/128 (one ulp there is 1/128), and subtracting
+// 65537 leaves (b - 128)/128 exactly -- every step is exact, so the bits are those of
+// unpack_u8 (b = 128 gives +0 either way).
+template <int K> __device__ __forceinline__ float unpack_u8_byte(uint32_t word)
+{
+    return fsub(__uint_as_float(__byte_perm(word, 0x47800000u, 0x7650 + K)), 65537.0f);
+}
+
 // src/filter.cpp:110-132, one sample of the FM discriminator.
 __device__ __forceinline__ float fm_discriminate(float ci, float cq, float pi_, float pq_)
 {

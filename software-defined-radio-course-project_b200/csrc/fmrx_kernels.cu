@@ -138,8 +138,200 @@ __global__ void __launch_bounds__(RF_THREADS) k_rf_demod(const RfDemodArgs a, co
     }
 }
 
+// ---- K1, register-window version (decimation known at compile time) ----------------
+//
+// Output n, tap k reads x[n*D - k].  A thread owns R = 4 consecutive outputs n..n+3, and
+// output n+i at tap k reads exactly the sample output n read at tap k - i*D.  So only
+// output n ("i = 0") loads from shared memory, one sample per plane per tap, into a
+// circular register delay line of L = 3*D entries; outputs n+1..n+3 take theirs from the
+// line, D, 2D and 3D taps back.  The tap loop is unrolled over one trip round the line so
+// that every line index is static.  Per tap: 2 sample LDS + 1 broadcast tap LDS against
+// 8 FMUL + 8 FADD -- FP32-pipe bound instead of shared-memory bound.  Each accumulator still
+// sees its products in ascending tap order.  T is padded to a multiple of L with zero
+// taps: acc + 0*x is a bit-exact no-op for finite x.  The planes are skewed by one word per
+// 4*D samples so that the lane stride (4*D + 1 words) is odd: conflict-free.
+
+constexpr int RFW_THREADS = 128;
+constexpr int RFW_R = 4;
+
+template <int D> struct RfWin {
+    static constexpr int L = (RFW_R - 1) * D;       // delay-line length
+    static constexpr int SEG = RFW_R * D;           // samples per thread = skew period
+    static int tpad(int T) { return (T + L - 1) / L * L; }
+    static int wp(int T) { return (RF_COMPUTED - 1) * D + T + (tpad(T) - T); }     // staged samples per plane
+    static int plane(int T) { return wp(T) + wp(T) / SEG + 2; }
+    static size_t smem_bytes(int T) { return sizeof(float) * ((size_t)2 * plane(T) + 2 * RF_COMPUTED + tpad(T)); }
+};
+
+template <int D> __global__ void __launch_bounds__(RFW_THREADS) k_rf_demod_win(const RfDemodArgs a)
+{
+    using W = RfWin<D>;
+    constexpr int L = W::L, SEG = W::SEG, R = RFW_R;
+    extern __shared__ float smem[];
+    const int T = a.T;
+    const int Tpad = (T + L - 1) / L * L;
+    const int padl = Tpad - T;                  // staged samples in front of the window (zeros)
+    const int Wp = (RF_COMPUTED - 1) * D + T + padl;
+    const int plane = Wp + Wp / SEG + 2;
+    float *s_i = smem;
+    float *s_q = s_i + plane;
+    float *o_i = s_q + plane;                   // [RF_COMPUTED]
+    float *o_q = o_i + RF_COMPUTED;
+    float *s_c = o_q + RF_COMPUTED;             // [Tpad]
+
+    const int c = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * RF_REAL;        // first demod sample of the tile
+    const long long n_pairs = (long long)a.n_if * D;
+    // staged element l' (0..Wp) is chunk-local pair m = m_base + l' - padl
+    const long long m_base = (long long)(n0 - 1) * D - (T - 1);
+    const uint8_t *iq = a.iq + (size_t)c * a.iq_stride;
+    const uint8_t *hist = a.hist + (size_t)c * 2 * a.hist_pairs;
+
+    for (int k = tid; k < Tpad; k += RFW_THREADS)
+        s_c[k] = (k < T) ? a.taps[k] : 0.0f;
+    // Staging: one aligned 32-bit load brings two IQ pairs; the loads of a batch are all
+    // issued before the first conversion so that their latencies overlap.  The `padl`
+    // elements in front of the window only ever meet zero taps, so they may hold whatever
+    // finite data lies there; words that straddle the chunk (history in front, nothing
+    // behind) are assembled pair by pair.
+    const uint16_t *iq16 = reinterpret_cast<const uint16_t *>(iq);
+    const uint16_t *hist16 = reinterpret_cast<const uint16_t *>(hist);
+    const long long m_first = m_base - padl;                    // pair index of l' = 0
+    const int lead = (int)((reinterpret_cast<uintptr_t>(iq16 + m_first) >> 1) & 1);   // pairs in front to reach 4-byte alignment
+    const long long m_word0 = m_first - lead;
+    const int n_words = (Wp + lead + 1) >> 1;
+    auto pair_at = [&](long long m) -> uint32_t {
+        if (m >= 0)
+            return m < n_pairs ? (uint32_t)iq16[m] : 0x8080u;      // (128,128) -> 0.0f, 0.0f
+        const long long h = a.hist_pairs + m;
+        return h >= 0 ? (uint32_t)hist16[h] : 0x8080u;
+    };
+    constexpr int BATCH = 5;
+    for (int j0 = tid; j0 < n_words; j0 += BATCH * RFW_THREADS) {
+        uint32_t v[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const int j = j0 + u * RFW_THREADS;
+            const long long m0 = m_word0 + 2 * (long long)j;
+            v[u] = 0x80808080u;
+            if (j < n_words) {
+                if (m0 >= 0 && m0 + 1 < n_pairs)
+                    v[u] = *reinterpret_cast<const uint32_t *>(iq16 + m0);
+                else
+                    v[u] = pair_at(m0) | (pair_at(m0 + 1) << 16);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const int lpa = 2 * (j0 + u * RFW_THREADS) - lead, lpb = lpa + 1;
+            if (lpa >= 0 && lpa < Wp) {
+                const int ad = lpa + lpa / SEG;
+                s_i[ad] = unpack_u8_byte<0>(v[u]);
+                s_q[ad] = unpack_u8_byte<1>(v[u]);
+            }
+            if (lpb < Wp) {
+                const int ad = lpb + lpb / SEG;
+                s_i[ad] = unpack_u8_byte<2>(v[u]);
+                s_q[ad] = unpack_u8_byte<3>(v[u]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // this thread: computed outputs o0..o0+3; sample of (i = 0, k = 0) sits at l' = b
+    const int o0 = tid * R;
+    const int b = o0 * D + (T - 1) + padl;      // == tid*SEG + (T - 1 + padl)
+    const int r0 = T - 1 + padl;                // b - tid*SEG: the same for every thread
+    // skewed address of l' = b + e is  tid*(SEG+1) + (r0 + e) + floor((r0 + e)/SEG)
+    const int tbase = tid * (SEG + 1);
+    (void)b;
+
+    float di[L], dq[L];                         // delay lines: slot (k mod L) holds the sample of tap k
+#pragma unroll
+    for (int m = 1; m <= L; m++) {              // "taps" -m: samples above b
+        const int e = r0 + m;
+        const int ad = tbase + e + e / SEG;
+        di[L - m] = s_i[ad];
+        dq[L - m] = s_q[ad];
+    }
+    float ai[R], aq[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        ai[i] = 0.0f;
+        aq[i] = 0.0f;
+    }
+    for (int k0 = 0; k0 < Tpad; k0 += L) {
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            const int e = r0 - (k0 + j);        // >= 0 by construction of padl
+            const int ad = tbase + e + e / SEG;
+            const float ck = s_c[k0 + j];
+            const float old_i = di[j], old_q = dq[j];          // tap k - L: output 3's sample
+            const float xi = s_i[ad], xq = s_q[ad];
+            di[j] = xi;
+            dq[j] = xq;
+            ai[0] = fadd(ai[0], fmul(ck, xi));
+            aq[0] = fadd(aq[0], fmul(ck, xq));
+            ai[1] = fadd(ai[1], fmul(ck, di[(j + L - D) % L]));
+            aq[1] = fadd(aq[1], fmul(ck, dq[(j + L - D) % L]));
+            ai[2] = fadd(ai[2], fmul(ck, di[(j + L - 2 * D) % L]));
+            aq[2] = fadd(aq[2], fmul(ck, dq[(j + L - 2 * D) % L]));
+            ai[3] = fadd(ai[3], fmul(ck, old_i));
+            aq[3] = fadd(aq[3], fmul(ck, old_q));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        o_i[o0 + i] = ai[i];
+        o_q[o0 + i] = aq[i];
+    }
+    __syncthreads();
+
+    float *demod = a.demod + (size_t)c * a.if_stride + a.if_off;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int o = tid + r * RFW_THREADS;    // coalesced
+        const int n = n0 - 1 + o;
+        if (o >= 1 && n < a.n_if) {
+            demod[n] = fm_discriminate(o_i[o], o_q[o], o_i[o - 1], o_q[o - 1]);
+            if (a.i_ds) {
+                const size_t g = (size_t)c * a.stage_stride + a.stage_off + n;
+                a.i_ds[g] = o_i[o];
+                a.q_ds[g] = o_q[o];
+            }
+        }
+    }
+}
+
+template <int D> static cudaError_t launch_rf_demod_win(const RfDemodArgs &a, int n_captures, cudaStream_t s)
+{
+    static size_t configured = 0;
+    const size_t smem = RfWin<D>::smem_bytes(a.T);
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_rf_demod_win<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return e;
+        configured = smem;
+    }
+    const int tiles = (a.n_if + RF_REAL - 1) / RF_REAL;
+    dim3 grid(tiles, n_captures);
+    k_rf_demod_win<D><<<grid, RFW_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rf_demod(const RfDemodArgs &a, int n_captures, cudaStream_t s)
 {
+    // the reference's modes decimate by 10, 4 and 9 (src/project.cpp:327-362)
+    static const bool ab_generic = getenv("FMRX_AB_RF_GENERIC") != nullptr;   // TEMP A/B
+    if (!ab_generic) {
+    if (a.decim == 10)
+        return launch_rf_demod_win<10>(a, n_captures, s);
+    if (a.decim == 4)
+        return launch_rf_demod_win<4>(a, n_captures, s);
+    if (a.decim == 9)
+        return launch_rf_demod_win<9>(a, n_captures, s);
+    }
     static size_t configured = 0;
     const size_t smem = rf_smem_bytes(a.T, a.decim);
     if (smem > configured) {
@@ -268,6 +460,7 @@ constexpr int PLL_CAND_WARPS = 8;        // warps 2,3,5,6,7,9,10,11: never on wa
 constexpr int PLL_IO_WARP = 1;           // warps 4 and 8 (warp 0's scheduler) only take part in the barriers
 constexpr int PLL_GROUP = 512;           // steps between checkpoints / barriers
 constexpr int PLL_RING = 4 * PLL_GROUP;  // per-sample input ring: 4 groups
+constexpr int kPllSpareSms = 32;         // SMs that must stay free for the FIR kernels before PLL CTAs claim whole SMs
 constexpr int PLL_TABLES = 32;           // candidate tables / phaseEst records in flight
 constexpr int PLL_LOOKBACK = 12;         // candidates for trigArg(u) are centred on phaseEst(u - PLL_LOOKBACK)
 constexpr int PLL_SPIN_LIMIT = 1 << 16;  // bounded polling (~1 ms): a bug must not hang the GPU
@@ -673,15 +866,39 @@ cudaError_t launch_pll(const PllArgs &a_in, int n_captures, cudaStream_t s)
 {
     PllArgs a = a_in;
     a.kconst = pllcore::trig_constants();
-    static bool configured = false;
-    const size_t dyn = sizeof(PllIn) * PLL_RING;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_pll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    // The chain warp's step time is pure issue-to-issue latency, and any other CTA resident
+    // on the same SM (the FIR kernels of the neighbouring chunks run concurrently on the
+    // other two streams) steals issue slots and shared-memory bandwidth from it: with 301
+    // taps that costs the PLL 34 % (profiles/r01_pll_sm_isolation.txt).  While there are SMs
+    // to spare, a PLL CTA therefore claims the whole shared memory of its SM, which keeps
+    // every other CTA off it.  With more captures than that leaves SMs for, it only asks
+    // for the ring it needs and shares.
+    static size_t ring_only = 0, whole_sm = 0;
+    static int sm_count = 0;
+    if (ring_only == 0) {
+        int dev = 0, optin = 0;
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess)
+            e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e == cudaSuccess)
+            e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess)
+            e = cudaFuncGetAttributes(&fa, k_pll);
         if (e != cudaSuccess)
             return e;
-        configured = true;
+        const size_t need = sizeof(PllIn) * PLL_RING;
+        size_t all = (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : 0;
+        if (all < need)
+            all = need;
+        e = cudaFuncSetAttribute(k_pll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)all);
+        if (e != cudaSuccess)
+            return e;
+        whole_sm = all;
+        ring_only = need;
     }
-    k_pll<<<n_captures, PLL_THREADS, dyn, s>>>(a);
+    const bool isolate = n_captures + kPllSpareSms <= sm_count;
+    k_pll<<<n_captures, PLL_THREADS, isolate ? whole_sm : ring_only, s>>>(a);
     return cudaGetLastError();
 }
 
