@@ -17,6 +17,7 @@
 // the reference's exact sequence -- so one MAC costs an FMUL and an FADD: the
 // attainable ceiling of these kernels is half the FFMA peak by construction.
 #include "fmrx_internal.h"
+#include <cstdio>   // TEMP debug
 
 namespace fmrx {
 
@@ -456,14 +457,21 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 
 constexpr int PLL_WARPS = 12;
 constexpr int PLL_THREADS = 32 * PLL_WARPS;
-constexpr int PLL_CAND_WARPS = 8;        // warps 2,3,5,6,7,9,10,11: never on warp 0's scheduler
-constexpr int PLL_IO_WARP = 1;           // warps 4 and 8 (warp 0's scheduler) only take part in the barriers
+constexpr int PLL_CAND_WARPS = 6;        // warps 2,3,6,7,10,11 (schedulers 2 and 3), two steps each: one per half-warp
+constexpr int PLL_CANDS = 16;            // grid points per candidate table
+constexpr int PLL_IO_WARPS = 3;          // warps 1,5,9 (scheduler 1); warps 4 and 8 (warp 0's scheduler) only take part in the barriers
 constexpr int PLL_GROUP = 512;           // steps between checkpoints / barriers
 constexpr int PLL_RING = 4 * PLL_GROUP;  // per-sample input ring: 4 groups
 constexpr int kPllSpareSms = 32;         // SMs that must stay free for the FIR kernels before PLL CTAs claim whole SMs
 constexpr int PLL_TABLES = 32;           // candidate tables / phaseEst records in flight
-constexpr int PLL_LOOKBACK = 12;         // candidates for trigArg(u) are centred on phaseEst(u - PLL_LOOKBACK)
+constexpr int PLL_LOOKBACK = 18;         // candidates for trigArg(u), u even, and trigArg(u+1) are centred on phaseEst(u - PLL_LOOKBACK):
+                                         // about three periods of the ripple the phase detector puts on phaseEst (half a pilot period)
 constexpr int PLL_SPIN_LIMIT = 1 << 16;  // bounded polling (~1 ms): a bug must not hang the GPU
+static_assert(PLL_TABLES == 32, "one phaseEst slot per lane of warp 0");
+static_assert(PLL_LOOKBACK % 2 == 0 && PLL_CANDS == 16, "two steps per candidate warp share one phaseEst record");
+constexpr int PLL_ABANDONED = 0x40000000;   // sequence numbers from here up say "group g was given up" (steps stay far below)
+constexpr int PLL_EXACT_MAX = 8;         // exact blocks (of 32) a speculated group may need before the next ones run unspeculated
+constexpr int PLL_BACKOFF_MAX = 8;       // groups run unspeculated between retries after repeated failures
 
 struct __align__(16) PllIn {             // off-chain inputs of one sample
     float x;
@@ -471,7 +479,7 @@ struct __align__(16) PllIn {             // off-chain inputs of one sample
     double xd;                           // (double)x
     double inv_x;                        // 1/(double)x, IEEE divide
     double v;                            // w * trigOffset after this step (:166-167)
-    int vi;                              // rint(v/ulp) for the binade the slot was prepared in ...
+    int vi16;                            // 16 * rint(v/ulp) for the binade the slot was prepared in (16 * : see pll_table_group) ...
     float vr;                            // ... and fl32(v/ulp - vi), |vr| <= 0.5
     int pad[2];
 };
@@ -499,15 +507,218 @@ __device__ __forceinline__ int2 ld_v2(const void *p)
 }
 __device__ __forceinline__ double i2d(int hi, int lo) { return __hiloint2double(hi, lo); }
 
+// ---- the table-speculated steps of one group (warp 0) --------------------------------
+//
+// One step: the loop filter (:163-164), the grid index of trigArg (:166-167), and the
+// lookup of Kp*errorD, Ki*errorD of the next sample in the candidate table of that grid
+// point.  No branches, no FP64 on the chain.  The grid index of trigArg(u) =
+// fl32(v(u) + phaseEst) is had without leaving the FP32 pipe: with v(u)/ulp = vi + vr
+// (integer + remainder, prepared per sample) and phaseEst/ulp = pi + t (pi = rint at the
+// group start, so |t| stays small),
+//     G = vi + pi + rint(t + vr),   t = fma(phaseEst, 1/ulp, -pi)  (one rounding).
+// Error budget, in grid steps: t carries one rounding (<= 2^-24 |t|), vr one (<= 2^-25), their
+// sum z one more (<= 2^-24 (|t| + 1/2)), and the reference's own double rounding of
+// v + phaseEst moves the exact sum by < 2^-29: together < 2^-23 |t| + 2^-24 + 2^-29.  A z
+// farther than 2^-22 * max(|t|, 4) from a tie therefore rounds the way the reference's sum
+// does; closer ones (about two per million steps) fail the guard and the group is redone
+// the exact way.
+struct TableRun {
+    float integ, ph, kpe, kie;       // in/out: loop filter state; Kp*errorD, Ki*errorD of the sample about to run
+    float inv_ulp_f, pi_f;           // 1/ulp (a power of two); rint(phaseEst/ulp) at the group start
+    int cu_base16;                   // 16 * the same rint as an integer
+    int base, cnt;                   // first step and number of steps of the group
+    unsigned in_base, tab_base, sg_base, sph_base;   // shared-window addresses: ring {vi, vr}, tables, parked indices, phaseEst records
+    int gi;                          // in: grid index of the trigArg before the group; out: of the last one
+    int n_exact;                     // out: blocks of 16 that had to be stepped the exact way
+    int fatal;                       // out: a block could not be completed here; the caller redoes the group
+    // for the exact steps
+    const PllIn *ring;               // the per-sample input ring
+    pllcore::Consts k;
+    double ulp;
+    float toff_base;                 // trigOffset before the group
+};
+
+// A block of up to 16 steps the exact way (the single-warp speculative step: sincos of the
+// known trigArg on the chain, ~300 cycles per step), from the state before the block:
+// the fall-back for a block in which a table was late, the grid point lay outside its
+// table, a candidate's guard failed or the grid index was too close to a tie.  Publishes
+// phaseEst and parks the grid indices exactly as the table steps do, and hands back
+// Kp*errorD, Ki*errorD of the sample after the block so that the table steps resume.
+// Returns false if one of ITS guards fails (the caller then redoes the whole group).
+__device__ __noinline__ bool pll_block_exact(TableRun &r, int u0, int nsteps, const int lane)
+{
+    using namespace pllcore;
+    const TrigK K = trig_constants();
+    int gi = r.gi;
+    Chain c;
+    c.integ = r.integ;
+    c.ph = r.ph;
+    c.toff = r.toff_base + (float)(u0 - r.base);     // only ever incremented here; v comes from the ring
+    c.tad = p_mul((double)gi, r.ulp);
+    c.fi = c.fq = 0.0f;
+    chain_refresh(c);
+    if (c.binade == FMRX_DISARMED || c.ulp != r.ulp)
+        return false;
+    bool ok = true;
+    for (int j = 0; j < nsteps; j++) {
+        const int u = u0 + j;
+        const PllIn i = r.ring[u & (PLL_RING - 1)];
+        StepIn in;
+        in.x = i.x;
+        in.xd = i.xd;
+        in.inv_x = i.inv_x;
+        in.turn = i2d(i.turn_hi, 0);
+        in.v = i.v;
+        ok &= chain_step_spec(c, r.k, K, in);
+        const int g = grid_index(grid_round(c.tad, c.inv_ulp));
+        if (lane == 0) {
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(r.sg_base + 4u * (unsigned)(u - r.base)), "r"(g) : "memory");
+            if ((u & 1) == 0)
+                asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(r.sph_base + (unsigned)(u & (PLL_TABLES - 1)) * 8u),
+                             "r"(__float_as_int(c.ph)), "r"(u + 1)
+                             : "memory");
+        }
+        gi = g;
+    }
+    // Kp*errorD, Ki*errorD of the sample after the block, from the now known trigArg
+    const PllIn nx = r.ring[(u0 + nsteps) & (PLL_RING - 1)];
+    const Feedback f = make_feedback(K, c.tad, i2d(nx.turn_hi, 0), nx.inv_x, nullptr, nullptr);
+    const float ed = error_from_feedback(f, nx.x, nx.xd, ok);
+    r.kpe = p_fmulf(r.k.kp, ed);
+    r.kie = p_fmulf(r.k.ki, ed);
+    r.integ = c.integ;
+    r.ph = c.ph;
+    r.gi = gi;
+    return ok;
+}
+
+template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
+{
+    using namespace pllcore;
+    float integ = r.integ, ph = r.ph, kpe = r.kpe, kie = r.kie;
+    const float inv_ulp_f = r.inv_ulp_f, pi_f = r.pi_f;
+    const int cu_base16 = r.cu_base16, base = r.base, cnt = r.cnt;
+    const unsigned in_base = r.in_base, tab_base = r.tab_base, sg_base = r.sg_base, sph_base = r.sph_base;
+    int bad = 0, gi = r.gi, n_exact = 0;
+    float worst = 0.0f;
+    // one step; vg = {vi, vr} of the sample, tab_a = address of its table row, sph_a = of its phaseEst record
+    auto step = [&](int u, unsigned tab_a, int2 vg, bool publish, unsigned sph_a) {
+        integ = p_faddf(integ, kie);                                  // :163
+        ph = p_faddf(ph, p_faddf(kpe, integ));                       // :164
+        const float tt = __fmaf_rn(ph, inv_ulp_f, -pi_f);
+        const float z = p_faddf(tt, __int_as_float(vg.y));
+        const float zm = p_faddf(z, 12582912.0f);                     // 1.5 * 2^23: rint in the low bits
+        // 16 * (vi + pi) is ready long before zm: the table address is two dependent integer
+        // operations behind zm (multiply-add, mask-and-merge), the grid index itself (:166-167)
+        // is only needed for the check
+        const int kk16 = vg.x + cu_base16;
+        gi = (__float_as_int(zm) - 0x4B400000) + (kk16 >> 4);
+        const unsigned addr = (((unsigned)__float_as_int(zm) * 16u + (unsigned)kk16) & (16 * PLL_CANDS - 16)) | tab_a;
+        // the candidate that IS trigArg(u) carries Kp*errorD, Ki*errorD of sample u+1 and proves it
+        int4 e;
+        asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(addr) : "memory");
+        kpe = __int_as_float(e.x);
+        kie = __int_as_float(e.y);
+        bad |= (e.z ^ gi) | (e.w ^ (u + 1));
+        const float frac = p_faddf(z, -p_faddf(zm, -12582912.0f));
+        worst = fmaxf(worst, __fmaf_rn(fmaxf(fabsf(tt), 4.0f), 0x1p-22f, fabsf(frac)));
+        // off the chain, every 2nd step: publish phaseEst(u) for later candidate tables.  (All
+        // lanes store the same record to the same address: one wavefront, and no branch or
+        // predicate on the chain.)
+        if (publish)
+            asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(sph_a), "r"(__float_as_int(ph)), "r"(u + 1) : "memory");
+    };
+    auto load_vg = [&](unsigned addr) {
+        int2 v;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+        return v;
+    };
+    // after a block: if a guard failed in it, the same block again, the exact way (rare)
+    auto settle = [&](int u0, int nb, float integ0, float ph0, int gi0) -> bool {
+        if (bad != 0 || !(worst < 0.5f)) {
+            r.integ = integ0;            // by value through r: nothing on the chain has its address taken
+            r.ph = ph0;
+            r.gi = gi0;
+            n_exact++;
+            if (!pll_block_exact(r, u0, nb, lane))
+                return false;
+            integ = r.integ;
+            ph = r.ph;
+            kpe = r.kpe;
+            kie = r.kie;
+            gi = r.gi;
+            bad = 0;
+            worst = 0.0f;
+        }
+        return true;
+    };
+    int t = 0;
+    bool fatal = false;
+    int2 vg0 = load_vg(in_base + (unsigned)(base & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
+    const int n_full = cnt >> 4;
+    for (int b = 0; b < n_full; b++, t += 16) {
+        const int u0 = base + t;
+        // the state before the block, in case it has to be stepped the exact way
+        const float integ0 = integ, ph0 = ph;
+        const int gi0 = gi;
+        // neither the rings nor the tables wrap inside a block of 16 (all sizes are multiples
+        // of 16 and u0 is one): addresses are base + constant
+        const unsigned in_a0 = in_base + (unsigned)(u0 & (PLL_RING - 1)) * (unsigned)sizeof(PllIn);
+        const unsigned tab_a0 = tab_base + (unsigned)(u0 & (PLL_TABLES - 1)) * (16u * PLL_CANDS);
+        const unsigned sph_a0 = sph_base + (unsigned)(u0 & (PLL_TABLES - 1)) * 8u;
+        const int2 vg_next_block = load_vg(in_base + (unsigned)((u0 + 16) & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
+        int gis[16];
+        int2 vg = vg0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const int2 vg_n = (j < 15) ? load_vg(in_a0 + (unsigned)(j + 1) * (unsigned)sizeof(PllIn)) : vg_next_block;
+            step(u0 + j, tab_a0 + (unsigned)j * (16u * PLL_CANDS), vg, (j & 1) == 0, sph_a0 + (unsigned)j * 8u);
+            gis[j] = gi;
+            vg = vg_n;
+        }
+        vg0 = vg_next_block;
+        // park the 16 grid indices for the I/O warp (every lane the same stores)
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(gis[j]), "r"(gis[j + 1]),
+                         "r"(gis[j + 2]), "r"(gis[j + 3])
+                         : "memory");
+        if (!settle(u0, 16, integ0, ph0, gi0)) {
+            fatal = true;
+            break;
+        }
+    }
+    if (!fatal && t < cnt) {     // the short last block of a launch
+        const int u0 = base + t, nb = cnt - t;
+        const float integ0 = integ, ph0 = ph;
+        const int gi0 = gi;
+        for (int j = 0; j < nb; j++) {
+            const int u = u0 + j;
+            const int2 vg = load_vg(in_base + (unsigned)(u & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
+            step(u, tab_base + (unsigned)(u & (PLL_TABLES - 1)) * (16u * PLL_CANDS), vg, (u & 1) == 0,
+                 sph_base + (unsigned)(u & (PLL_TABLES - 1)) * 8u);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(gi) : "memory");
+        }
+        fatal = !settle(u0, nb, integ0, ph0, gi0);
+    }
+    r.fatal = fatal;
+    r.integ = integ;
+    r.ph = ph;
+    r.kpe = kpe;
+    r.kie = kie;
+    r.gi = gi;
+    r.n_exact = n_exact;
+}
+
 __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
 {
     using namespace pllcore;
     extern __shared__ __align__(16) unsigned char pll_dyn_smem[];
     PllIn *s_in = reinterpret_cast<PllIn *>(pll_dyn_smem);      // [PLL_RING]
-    __shared__ int4 s_ph[PLL_TABLES];                 // {phaseEst lo, hi, seq, -}: published by warp 0
+    __shared__ int2 s_ph[PLL_TABLES];                 // {phaseEst, step + 1} published by warp 0; {-, PLL_ABANDONED + g}: group g given up
     // candidate tables, indexed by (step & 15, grid index & 31): {Kp*errorD, Ki*errorD of the next
     // sample, grid index, step+1 (negated if a guard failed)}; one self-validating 16-byte record per lane
-    __shared__ int4 s_tab[PLL_TABLES][32];
+    __shared__ int4 s_tab[PLL_TABLES][PLL_CANDS];
     __shared__ __align__(16) int s_g[2][PLL_GROUP];                 // grid index of each trigArg of the group, double-buffered
     __shared__ double s_grid[2];                      // ulp, 1/ulp of the current group
     __shared__ double s_prep_ulp[4];                  // ulp the ring slots of each group were prepared with
@@ -532,12 +743,14 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     const float toff0 = st[5];
     const bool regular = toff_is_regular(toff0);
     const int t0 = regular ? (int)toff0 : 0;
-    // candidate warps: 2,3,5,6,7,9,10,11 -> 0..7
-    const int cand_id = warp - 2 - (warp >> 2);
+    // roles by scheduler (warp & 3): 0 = the chain (warp 0; warps 4, 8 idle), 1 = I/O, 2 and 3 = candidates
+    const int role = warp & 3;
+    const int io_id = warp >> 2;                          // 0..2 for warps 1, 5, 9
+    const int cand_id = (warp >> 2) * 2 + role - 2;       // 0..5 for warps 2, 3, 6, 7, 10, 11
 
     // I/O warp: one lane per sample, off-chain inputs of the samples of a group into the ring
     auto prepare = [&](int base) {
-        for (int j = 0; j < PLL_GROUP; j += 32) {
+        for (int j = 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS) {
             const int u = base + j + lane;
             const float pvv = (u < n) ? p[u] : 1.0f;
             PllIn in;
@@ -549,19 +762,19 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             in.v = __dmul_rn(k.w, (double)toff);
             // v on the float grid of the current binade: integer part and remainder
             const double qv = grid_round(in.v, s_grid[1]);
-            in.vi = grid_index(qv);
+            in.vi16 = grid_index(qv) << 4;
             in.vr = __double2float_rn(__fma_rn(in.v, s_grid[1], -p_add(qv, -FMRX_RINT_MAGIC)));
             in.pad[0] = in.pad[1] = 0;
             s_in[u & (PLL_RING - 1)] = in;
         }
-        if (lane == 0)
+        if (lane == 0 && io_id == 0)
             s_prep_ulp[(base / PLL_GROUP) & 3] = s_grid[0];
     };
 
     if (threadIdx.x < PLL_TABLES)
-        s_ph[threadIdx.x] = make_int4(0, 0, (int)0x80000000, 0);
-    for (int i = threadIdx.x; i < PLL_TABLES * 32; i += PLL_THREADS)
-        s_tab[i >> 5][i & 31] = make_int4(0, 0, 0, (int)0x80000000);
+        s_ph[threadIdx.x] = make_int2(0, 0);
+    for (int i = threadIdx.x; i < PLL_TABLES * PLL_CANDS; i += PLL_THREADS)
+        s_tab[i / PLL_CANDS][i % PLL_CANDS] = make_int4(0, 0, 0, (int)0x80000000);
     if (threadIdx.x == 0)
         s_flag[1] = 0;
     // warp 0 owns the recurrence state
@@ -571,7 +784,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     float kpe_next = 0.0f, kie_next = 0.0f;
     bool dead = false;               // a hand-off timed out: stay on the checked path
     int backoff = 0, skip = 0;       // after a failed group: run `skip` groups checked, then retry
-    int n_groups = 0, n_redone = 0, n_tab = 0, n_frac = 0;
+    int n_groups = 0, n_redone = 0, n_exact = 0;
+    long long dbg_cyc = 0;
+    int dbg_steps = 0;
     if (warp == 0) {
         ch.integ = st[0];
         ch.ph = st[1];
@@ -585,7 +800,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         }
     }
     __syncthreads();
-    if (warp == PLL_IO_WARP) {
+    if (role == 1) {
         prepare(0);
         prepare(PLL_GROUP);
     }
@@ -604,9 +819,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 s_grid[0] = ch.ulp;
                 s_grid[1] = ch.inv_ulp;
                 // phaseEst "of steps base-L .. base-1" for the first candidate tables
-                const double phd = (double)ch.ph;
-                for (int j = 1; j <= PLL_LOOKBACK + 3; j++)
-                    s_ph[(base - j) & (PLL_TABLES - 1)] = make_int4(__double2loint(phd), __double2hiint(phd), base - j + 1, 0);
+                for (int j = 1; j <= PLL_LOOKBACK; j++)
+                    s_ph[(base - j) & (PLL_TABLES - 1)] = make_int2(__float_as_int(ch.ph), base - j + 1);
             }
         }
         __syncthreads();
@@ -627,15 +841,6 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     kpe = p_fmulf(k.kp, ed);
                     kie = p_fmulf(k.ki, ed);
                 }
-                // The grid index of trigArg(u) = fl32(v(u) + phaseEst) without leaving the FP32
-                // pipe: with v(u)/ulp = vi + vr (integer + remainder, prepared per sample) and
-                // phaseEst/ulp = pi + t (pi = rint, at the group start, so |t| stays small),
-                //     G = vi + pi + rint(t + vr),   t = fma(phaseEst, 1/ulp, -pi)  (one rounding)
-                // The roundings of t, of t + vr and of vr together stay below 2^-21.5 * max(|t|, 1) of
-                // a grid step (and the reference's own double rounding of v + phaseEst moves the sum
-                // by < 2^-29), so a sum farther than 2^-20 * max(|t|, 4) from a tie rounds the same
-                // way; closer ones (a few per million steps) fail the guard and the group is redone
-                // the exact way.
                 const float inv_ulp_f = (float)inv_ulp;                          // a power of two
                 float pi_f = 0.0f;
                 int cu_base = 0;
@@ -664,98 +869,69 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                             s_flag[1] = 1;
                     }
                 }
-                int bad = 0;                 // OR of (table key ^ expected key) over the steps
-                float worst = 0.0f;          // max of |frac| + margin over the steps; must stay < 0.5
-                int gi = 0;
-                // one step: loop filter, grid index, table lookup.  No branches, no FP64 on the chain.
-                // in_a = shared address of this sample's ring slot, tab_a = of its table row.
-                auto step = [&](int u, unsigned in_a, unsigned tab_a, int2 vg, bool publish) {
-                    integ = p_faddf(integ, kie);                                  // :163
-                    ph = p_faddf(ph, p_faddf(kpe, integ));                       // :164
-                    const float tt = __fmaf_rn(ph, inv_ulp_f, -pi_f);
-                    const float z = p_faddf(tt, __int_as_float(vg.y));
-                    const float zm = p_faddf(z, 12582912.0f);                     // 1.5 * 2^23: rint in the low bits
-                    gi = __float_as_int(zm) + (vg.x + cu_base);                   // :166-167 as a grid index
-                    // the candidate that IS trigArg(u) carries Kp*errorD, Ki*errorD of sample u+1 and proves it
-                    int4 e;
-                    asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
-                                 : "r"(((gi << 4) & 0x1f0) | tab_a)
-                                 : "memory");
-                    kpe = __int_as_float(e.x);
-                    kie = __int_as_float(e.y);
-                    bad |= (e.z ^ gi) | (e.w ^ (u + 1));
-                    // rounding budget: < 2^-21.5 * max(|t|, 1) of a grid step; margin 2^-20 * max(|t|, 4)
-                    const float frac = p_faddf(z, -p_faddf(zm, -12582912.0f));
-                    worst = fmaxf(worst, __fmaf_rn(fmaxf(fabsf(tt), 4.0f), 0x1p-20f, fabsf(frac)));
-                    // off the chain, every 4th step: publish phaseEst(u) for later candidate tables
-                    if (publish && lane == 0) {
-                        const double phd = (double)ph;
-                        st_v4(&s_ph[u & (PLL_TABLES - 1)], __double2loint(phd), __double2hiint(phd), u + 1, 0);
-                    }
-                    (void)in_a;
-                };
-                auto load_vg = [&](unsigned addr) {
-                    int2 v;
-                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-                    return v;
-                };
-                const unsigned in_base = smem_u32(&s_in[0]) + 32u;               // offset of {vi, vr} in a slot
-                const unsigned tab_base = smem_u32(&s_tab[0][0]);
-                int t = 0;
+                // the steps themselves: a separately compiled function, so that its instruction
+                // schedule -- which IS the step time -- does not move when anything else in this
+                // kernel changes
+                TableRun r;
+                r.integ = integ;
+                r.ph = ph;
+                r.kpe = kpe;
+                r.kie = kie;
+                r.inv_ulp_f = inv_ulp_f;
+                r.pi_f = pi_f;
+                r.cu_base16 = (cu_base + 0x4B400000) << 4;                      // 16 * rint(phaseEst/ulp), |.| < 2^25
+                r.base = base;
+                r.cnt = cnt;
+                r.in_base = smem_u32(&s_in[0]) + 32u;                            // offset of {vi, vr} in a slot
+                r.tab_base = smem_u32(&s_tab[0][0]);
+                r.sg_base = smem_u32(&s_g[g & 1][0]);
+                r.sph_base = smem_u32(&s_ph[0]);
+                r.gi = __double2int_rn(p_mul(ch.tad, inv_ulp));                  // exact: trigArg is on the grid
+                r.n_exact = 0;
+                r.fatal = 0;
+                r.ring = s_in;
+                r.k = k;
+                r.ulp = ulp;
+                r.toff_base = ch.toff;
                 if (good) {
-                    int2 vg0 = load_vg(in_base + (unsigned)(base & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
-                    for (; t + 16 <= cnt; t += 16) {
-                        const int u0 = base + t;
-                        // neither the ring nor the table wraps inside a block of 16 (both sizes are
-                        // multiples of 16 and u0 is one): addresses are base + constant
-                        const unsigned in_a0 = in_base + (unsigned)(u0 & (PLL_RING - 1)) * (unsigned)sizeof(PllIn);
-                        const unsigned tab_a0 = tab_base + (unsigned)(u0 & (PLL_TABLES - 1)) * 512u;
-                        const int2 vg_next_block =
-                            load_vg(in_base + (unsigned)((u0 + 16) & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
-                        int gis[16];
-                        int2 vg = vg0;
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const int2 vg_n = (j < 15) ? load_vg(in_a0 + (unsigned)(j + 1) * (unsigned)sizeof(PllIn)) : vg_next_block;
-                            step(u0 + j, 0u, tab_a0 + (unsigned)j * 512u, vg, (j & 3) == 0);
-                            gis[j] = gi;
-                            vg = vg_n;
-                        }
-                        vg0 = vg_next_block;
-                        if (lane == 0) {     // park the 16 grid indices for the I/O warp
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4)
-                                *reinterpret_cast<int4 *>(&s_g[g & 1][t + j]) = make_int4(gis[j], gis[j + 1], gis[j + 2], gis[j + 3]);
-                        }
-                    }
-                    for (; t < cnt; t++) {   // tail of the last group of a launch
-                        const int u = base + t;
-                        const int2 vg = load_vg(in_base + (unsigned)(u & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
-                        step(u, 0u, tab_base + (unsigned)(u & (PLL_TABLES - 1)) * 512u, vg, (u & 3) == 0);
-                        if (lane == 0)
-                            s_g[g & 1][t] = gi;
-                    }
-                    good = good && bad == 0 && worst < 0.5f;
+                    __syncwarp();
+                    const long long c0 = clock64();
+                    if ((a.variant & 255) == 1)
+                        pll_table_group<1>(r, lane);
+                    else
+                        pll_table_group<0>(r, lane);
+                    const long long c1 = clock64();
+                    dbg_cyc += c1 - c0;
+                    dbg_steps += cnt;
+                    good = r.fatal == 0;
+                    n_exact += r.n_exact;
                 }
-                n_tab += (bad != 0); n_frac += !(worst < 0.5f);
                 if (good) {
-                    ch.integ = integ;
-                    ch.ph = ph;
+                    ch.integ = r.integ;
+                    ch.ph = r.ph;
                     ch.toff = (float)min(t0 + base + cnt, 16777216);
-                    ch.tad = p_mul((double)gi, ulp);
+                    ch.tad = p_mul((double)r.gi, ulp);
                     stale = true;
                     have_ed = true;
-                    kpe_next = kpe;
-                    kie_next = kie;
-                    backoff = 0;
+                    kpe_next = r.kpe;
+                    kie_next = r.kie;
+                    // a group that needed many exact blocks is no faster than a checked one:
+                    // back off like after a failure, but keep its (exact) result
+                    if (r.n_exact > PLL_EXACT_MAX) {
+                        backoff = min(backoff ? 2 * backoff : 1, PLL_BACKOFF_MAX);
+                        skip = backoff;
+                    } else {
+                        backoff = 0;
+                    }
                 }
             }
             if (!good) {
                 if (spec) {
+                    // the candidate warps stop polling for this group: every phaseEst slot says so
+                    asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(smem_u32(&s_ph[lane])), "r"(0), "r"(PLL_ABANDONED + g) : "memory");
                     n_redone++;
-                    backoff = min(backoff ? 2 * backoff : 1, 64);
-                    skip = backoff;
+                    backoff = min(backoff ? 2 * backoff : 1, PLL_BACKOFF_MAX);
+                    skip = backoff - 1;
                 } else if (skip > 0) {
                     skip--;
                 }
@@ -797,41 +973,52 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 s_spec[g & 1] = good ? 1 : 0;
                 s_ulp_hist[g & 1] = ulp;
             }
-        } else if ((warp & 3) != 0 && warp != PLL_IO_WARP) {
-            // ================= candidate tables: warp cand_id takes steps t = cand_id (mod PLL_CAND_WARPS) =================
+        } else if (role >= 2) {
+            // ================= candidate tables =================
+            // A warp evaluates two consecutive steps at once, one per half-warp (16 grid points
+            // each): steps base + 2*cand_id + {0, 1} (mod 2*PLL_CAND_WARPS).  Both need the same
+            // phaseEst record (every 4th step is published and the first of the two is even).
             if (spec) {
-                for (int t = cand_id; t < cnt; t += PLL_CAND_WARPS) {
-                    const int u = base + t;
+                const int half = lane >> 4, hl = lane & (PLL_CANDS - 1);
+                for (int t2 = 2 * cand_id; t2 < cnt; t2 += 2 * PLL_CAND_WARPS) {
+                    const bool live = t2 + half < cnt;
+                    const int u = base + t2 + (live ? half : 0);
                     const double v = s_in[u & (PLL_RING - 1)].v;
                     const PllIn nx = s_in[(u + 1) & (PLL_RING - 1)];     // the sample the result is for
-                    // phaseEst of the latest published step at or before u - PLL_LOOKBACK (every 4th is)
-                    const int ur = (u - PLL_LOOKBACK) & ~3;
-                    int4 pr = ld_v4(&s_ph[ur & (PLL_TABLES - 1)]);
-                    for (int spin = 0; pr.z != ur + 1 && spin < PLL_SPIN_LIMIT; spin++)
-                        pr = ld_v4(&s_ph[ur & (PLL_TABLES - 1)]);
-                    if (pr.z != ur + 1) {
-                        s_flag[1] = 1;           // gave up: warp 0 will see missing tables and redo
+                    const int ur = base + t2 - PLL_LOOKBACK;             // even: published
+                    // poll while the slot still holds an older record
+                    int2 pr = ld_v2(&s_ph[ur & (PLL_TABLES - 1)]);
+                    for (int spin = 0; pr.y - (ur + 1) < 0 && spin < PLL_SPIN_LIMIT; spin++)
+                        pr = ld_v2(&s_ph[ur & (PLL_TABLES - 1)]);
+
+                    if (pr.y >= PLL_ABANDONED)       // warp 0 gave the group up
+                        break;
+                    if (pr.y - (ur + 1) > 0)         // this warp fell a whole ring behind and the record is gone: skip the
+                        continue;                    // pair (warp 0 steps that block the exact way) rather than wait for ever
+                    if (pr.y != ur + 1) {
+                        s_flag[1] = 1;               // gave up: warp 0 will see missing tables
                         break;
                     }
-                    // this lane's grid point: the one congruent to `lane` (mod 32) in [G_c-16, G_c+15]
-                    const int gc = grid_index(grid_round(p_add(v, i2d(pr.y, pr.x)), inv_ulp));
-                    const int gl = gc - 16 + ((lane - (gc - 16)) & 31);
+                    // this lane's grid point: the one congruent to `hl` (mod 16) in [G_c-8, G_c+7]
+                    const int gc = grid_index(grid_round(p_add(v, (double)__int_as_float(pr.x)), inv_ulp));
+                    const int gl = gc - PLL_CANDS / 2 + ((hl - (gc - PLL_CANDS / 2)) & (PLL_CANDS - 1));
                     const double tad = p_mul((double)gl, ulp);                        // exact
                     const Feedback f = make_feedback(K, tad, i2d(nx.turn_hi, 0), nx.inv_x, nullptr, nullptr);
                     // the float grid of the binade is only right strictly inside it
                     const int ag = gl < 0 ? -gl : gl;
                     bool ok = ag > (1 << 23) && ag < (1 << 24);
                     const float ed = error_from_feedback(f, nx.x, nx.xd, ok);         // :159-161 of sample u+1
-                    st_v4(&s_tab[u & (PLL_TABLES - 1)][lane], __float_as_int(p_fmulf(k.kp, ed)), __float_as_int(p_fmulf(k.ki, ed)), gl,
-                          ok ? u + 1 : -(u + 1));
+                    if (live)
+                        st_v4(&s_tab[u & (PLL_TABLES - 1)][hl], __float_as_int(p_fmulf(k.kp, ed)), __float_as_int(p_fmulf(k.ki, ed)), gl,
+                              ok ? u + 1 : -(u + 1));
                 }
             }
-        } else if (warp == PLL_IO_WARP) {
+        } else if (role == 1) {
             // ================= I/O =================
             prepare(base + 2 * PLL_GROUP);
             if (g > 0) {                     // previous group: always complete
                 const int pb = base - PLL_GROUP;
-                for (int j = lane; j < PLL_GROUP; j += 32)
+                for (int j = lane + 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS)
                     tr[pb + j] = s_spec[(g - 1) & 1] ? __double2float_rn(p_mul((double)s_g[(g - 1) & 1][j], s_ulp_hist[(g - 1) & 1]))
                                                      : __int_as_float(s_g[(g - 1) & 1][j]);
             }
@@ -839,7 +1026,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         __syncthreads();
     }
     // the last group's trigArg
-    if (warp == PLL_IO_WARP && n > 0) {
+    if (warp == 1 && n > 0) {
         const int g = (n - 1) / PLL_GROUP, pb = g * PLL_GROUP;
         for (int j = lane; pb + j < n && j < PLL_GROUP; j += 32)
             tr[pb + j] = s_spec[g & 1] ? __double2float_rn(p_mul((double)s_g[g & 1][j], s_ulp_hist[g & 1]))
@@ -855,8 +1042,11 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         st[2] = fi;
         st[3] = fq;
         st[5] = ch.toff;
-        st[6] = (float)(n_groups + 1000 * n_tab);     // diagnostics of the last launch
-        st[7] = s_flag[1] ? -1.0f : (float)(n_redone + 1000 * n_frac);
+        if ((a.variant & 256) && c == 0)
+            printf("pll dbg: groups %d exact blocks %d redone %d | %.1f cyc/step over %d table steps\n", n_groups, n_exact, n_redone,
+                   dbg_steps ? (double)dbg_cyc / dbg_steps : 0.0, dbg_steps);
+        st[6] = (float)(n_groups + 1000 * min(n_exact, 999));     // diagnostics of the last launch
+        st[7] = s_flag[1] ? -1.0f : (float)n_redone;
         if (n > 0)
             st[4] = nco_from_trig(__double2float_rn(ch.tad), a.prm.scale, a.prm.adjust);   // :173
     }
@@ -866,6 +1056,8 @@ cudaError_t launch_pll(const PllArgs &a_in, int n_captures, cudaStream_t s)
 {
     PllArgs a = a_in;
     a.kconst = pllcore::trig_constants();
+    static const int variant = getenv("FMRX_PLL_VARIANT") ? atoi(getenv("FMRX_PLL_VARIANT")) : 0;   // TEMP A/B
+    a.variant = variant;
     // The chain warp's step time is pure issue-to-issue latency, and any other CTA resident
     // on the same SM (the FIR kernels of the neighbouring chunks run concurrently on the
     // other two streams) steals issue slots and shared-memory bandwidth from it: with 301
