@@ -460,17 +460,17 @@ constexpr int PLL_THREADS = 32 * PLL_WARPS;
 constexpr int PLL_CAND_WARPS = 6;        // warps 2,3,6,7,10,11 (schedulers 2 and 3), two steps each: one per half-warp
 constexpr int PLL_CANDS = 16;            // grid points per candidate table
 constexpr int PLL_IO_WARPS = 3;          // warps 1,5,9 (scheduler 1); warps 4 and 8 (warp 0's scheduler) only take part in the barriers
-constexpr int PLL_GROUP = 512;           // steps between checkpoints / barriers
+constexpr int PLL_GROUP = 1024;          // steps between checkpoints / barriers
 constexpr int PLL_RING = 4 * PLL_GROUP;  // per-sample input ring: 4 groups
 constexpr int kPllSpareSms = 32;         // SMs that must stay free for the FIR kernels before PLL CTAs claim whole SMs
 constexpr int PLL_TABLES = 32;           // candidate tables / phaseEst records in flight
 constexpr int PLL_LOOKBACK = 18;         // candidates for trigArg(u), u even, and trigArg(u+1) are centred on phaseEst(u - PLL_LOOKBACK):
                                          // about three periods of the ripple the phase detector puts on phaseEst (half a pilot period)
 constexpr int PLL_SPIN_LIMIT = 1 << 16;  // bounded polling (~1 ms): a bug must not hang the GPU
-static_assert(PLL_TABLES == 32, "one phaseEst slot per lane of warp 0");
+static_assert(PLL_TABLES == 32 && PLL_LOOKBACK <= 32, "one phaseEst slot, one awaited table per lane of warp 0");
 static_assert(PLL_LOOKBACK % 2 == 0 && PLL_CANDS == 16, "two steps per candidate warp share one phaseEst record");
 constexpr int PLL_ABANDONED = 0x40000000;   // sequence numbers from here up say "group g was given up" (steps stay far below)
-constexpr int PLL_EXACT_MAX = 8;         // exact blocks (of 32) a speculated group may need before the next ones run unspeculated
+constexpr int PLL_EXACT_MAX = PLL_GROUP / 64;   // exact blocks (a quarter of the group) a speculated group may need before the next ones run unspeculated
 constexpr int PLL_BACKOFF_MAX = 8;       // groups run unspeculated between retries after repeated failures
 
 struct __align__(16) PllIn {             // off-chain inputs of one sample
@@ -785,7 +785,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     bool dead = false;               // a hand-off timed out: stay on the checked path
     int backoff = 0, skip = 0;       // after a failed group: run `skip` groups checked, then retry
     int n_groups = 0, n_redone = 0, n_exact = 0;
-    long long dbg_cyc = 0;
+    long long dbg_cyc = 0, dbg_wait = 0, dbg_pre = 0, dbg_bar = 0;
+    const long long dbg_k0 = clock64();
+    const int n_groups_all = (n + PLL_GROUP - 1) / PLL_GROUP;
     int dbg_steps = 0;
     if (warp == 0) {
         ch.integ = st[0];
@@ -826,6 +828,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         __syncthreads();
         const bool spec = s_flag[0] != 0;
         const double ulp = s_grid[0], inv_ulp = s_grid[1];
+        const long long dbg_ga = clock64();
 
         if (warp == 0) {
             // ================= the chain =================
@@ -854,12 +857,15 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 recentre();
                 // wait (bounded) for the first tables of the group; afterwards the candidate
                 // warps run ahead and a late table only clears `good`
-                for (int t = 0; t < PLL_LOOKBACK && t < cnt; t++) {
-                    const int want = base + t + 1;
+                const long long dbg_w0 = clock64();
+                dbg_pre += dbg_w0 - dbg_ga;
+                {   // lane t watches table t
+                    const int want = base + lane + 1;
+                    const bool need = lane < PLL_LOOKBACK && lane < cnt;
                     int spin = 0;
                     for (;;) {
-                        const int z = ld_v4(&s_tab[(base + t) & (PLL_TABLES - 1)][0]).w;
-                        if (z == want || z == -want || ++spin >= PLL_SPIN_LIMIT)
+                        const int z = ld_v4(&s_tab[(base + lane) & (PLL_TABLES - 1)][0]).w;
+                        if (__all_sync(0xffffffffu, !need || z == want || z == -want) || ++spin >= PLL_SPIN_LIMIT)
                             break;
                     }
                     if (spin >= PLL_SPIN_LIMIT) {
@@ -869,6 +875,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                             s_flag[1] = 1;
                     }
                 }
+                dbg_wait += clock64() - dbg_w0;
                 // the steps themselves: a separately compiled function, so that its instruction
                 // schedule -- which IS the step time -- does not move when anything else in this
                 // kernel changes
@@ -987,6 +994,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const PllIn nx = s_in[(u + 1) & (PLL_RING - 1)];     // the sample the result is for
                     const int ur = base + t2 - PLL_LOOKBACK;             // even: published
                     // poll while the slot still holds an older record
+                    const long long dbg_q0 = clock64();
                     int2 pr = ld_v2(&s_ph[ur & (PLL_TABLES - 1)]);
                     for (int spin = 0; pr.y - (ur + 1) < 0 && spin < PLL_SPIN_LIMIT; spin++)
                         pr = ld_v2(&s_ph[ur & (PLL_TABLES - 1)]);
@@ -1008,6 +1016,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const int ag = gl < 0 ? -gl : gl;
                     bool ok = ag > (1 << 23) && ag < (1 << 24);
                     const float ed = error_from_feedback(f, nx.x, nx.xd, ok);         // :159-161 of sample u+1
+                    if (t2 < 12) { dbg_pre += dbg_q0 - dbg_ga; dbg_wait += clock64() - dbg_q0; }
+                    else if (t2 < 24) { dbg_cyc += clock64() - dbg_q0; dbg_steps++; }
                     if (live)
                         st_v4(&s_tab[u & (PLL_TABLES - 1)][hl], __float_as_int(p_fmulf(k.kp, ed)), __float_as_int(p_fmulf(k.ki, ed)), gl,
                               ok ? u + 1 : -(u + 1));
@@ -1032,6 +1042,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             tr[pb + j] = s_spec[g & 1] ? __double2float_rn(p_mul((double)s_g[g & 1][j], s_ulp_hist[g & 1]))
                                        : __int_as_float(s_g[g & 1][j]);
     }
+    if ((a.variant & 256) && c == 0 && (warp == 2 || warp == 11) && lane == 0)
+        printf("pll dbg cand warp %d: first round starts %.0f after the barrier and takes %.0f; second round (incl. wait) %.0f\n", warp,
+               (double)dbg_pre / n_groups_all, (double)dbg_wait / n_groups_all, dbg_steps ? (double)dbg_cyc / dbg_steps : 0.0);
     if (warp == 0 && lane == 0) {
         if (stale)
             chain_refresh(ch);
@@ -1043,8 +1056,10 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         st[3] = fq;
         st[5] = ch.toff;
         if ((a.variant & 256) && c == 0)
-            printf("pll dbg: groups %d exact blocks %d redone %d | %.1f cyc/step over %d table steps\n", n_groups, n_exact, n_redone,
-                   dbg_steps ? (double)dbg_cyc / dbg_steps : 0.0, dbg_steps);
+            printf("pll dbg: groups %d exact blocks %d redone %d | %.1f cyc/step over %d table steps | kernel %.1f cyc/step; per group: before wait %.0f, wait for tables %.0f, steps %.0f, rest %.0f\n",
+                   n_groups, n_exact, n_redone, dbg_steps ? (double)dbg_cyc / dbg_steps : 0.0, dbg_steps, (double)(clock64() - dbg_k0) / n,
+                   (double)dbg_pre / n_groups, (double)dbg_wait / n_groups, (double)dbg_cyc / n_groups,
+                   (double)(clock64() - dbg_k0 - dbg_pre - dbg_wait - dbg_cyc) / n_groups);
         st[6] = (float)(n_groups + 1000 * min(n_exact, 999));     // diagnostics of the last launch
         st[7] = s_flag[1] ? -1.0f : (float)n_redone;
         if (n > 0)

@@ -10,4 +10,4 @@ for l in sys.stdin:
               d["pll_groups_redone_last_chunk"], "rf", round(d["rf_demod_ms"], 2), "bp", round(d["bandpass_ms"], 2), "au",
               round(d["audio_ms"], 2))
     elif l.startswith("pll dbg:"):
-        print(l[:230])
+        print(l[:330])
