@@ -459,19 +459,20 @@ constexpr int PLL_WARPS = 12;
 constexpr int PLL_THREADS = 32 * PLL_WARPS;
 constexpr int PLL_CAND_WARPS = 6;        // warps 2,3,6,7,10,11 (schedulers 2 and 3), two steps each: one per half-warp
 constexpr int PLL_CANDS = 16;            // grid points per candidate table
-constexpr int PLL_IO_WARPS = 3;          // warps 1,5,9 (scheduler 1); warps 4 and 8 (warp 0's scheduler) only take part in the barriers
+constexpr int PLL_IO_WARPS = 2;          // warps 1, 5 (scheduler 1); warps 4 and 8 (warp 0's scheduler) only take part in the barriers
+constexpr int PLL_PRED_WARP = 9;         // the run-ahead predictor (scheduler 1)
 constexpr int PLL_GROUP = 1024;          // steps between checkpoints / barriers
 constexpr int PLL_RING = 4 * PLL_GROUP;  // per-sample input ring: 4 groups
 constexpr int kPllSpareSms = 32;         // SMs that must stay free for the FIR kernels before PLL CTAs claim whole SMs
-constexpr int PLL_TABLES = 32;           // candidate tables / phaseEst records in flight
-constexpr int PLL_LOOKBACK = 18;         // candidates for trigArg(u), u even, and trigArg(u+1) are centred on phaseEst(u - PLL_LOOKBACK):
-                                         // about three periods of the ripple the phase detector puts on phaseEst (half a pilot period)
+constexpr int PLL_TABLES = 64;           // candidate tables in flight (a ring over the steps)
+constexpr int PLL_PH_RING = 256;         // predicted-phaseEst records in flight
+constexpr int PLL_PRED_LEAD = 128;       // the predictor stays at most this far ahead of warp 0
 constexpr int PLL_SPIN_LIMIT = 1 << 16;  // bounded polling (~1 ms): a bug must not hang the GPU
-static_assert(PLL_TABLES == 32 && PLL_LOOKBACK <= 32, "one phaseEst slot, one awaited table per lane of warp 0");
-static_assert(PLL_LOOKBACK % 2 == 0 && PLL_CANDS == 16, "two steps per candidate warp share one phaseEst record");
-constexpr int PLL_ABANDONED = 0x40000000;   // sequence numbers from here up say "group g was given up" (steps stay far below)
-constexpr int PLL_EXACT_MAX = PLL_GROUP / 64;   // exact blocks (a quarter of the group) a speculated group may need before the next ones run unspeculated
-constexpr int PLL_BACKOFF_MAX = 8;       // groups run unspeculated between retries after repeated failures
+static_assert(PLL_CANDS == 16 && PLL_TABLES % 16 == 0 && PLL_PH_RING % 2 == 0, "two steps per candidate warp; no ring wraps inside a block of 16");
+static_assert(PLL_PRED_LEAD + 2 * PLL_TABLES <= PLL_PH_RING, "a record outlives every candidate that may still need it");
+constexpr int PLL_ABANDONED = -1;        // progress value: warp 0 gave the group up
+constexpr int PLL_EXACT_MAX = PLL_GROUP / 128;  // exact blocks (an eighth of the group) after which a speculated group is given up
+constexpr int PLL_BACKOFF_MAX = 64;      // groups run unspeculated between retries after repeated failures
 
 struct __align__(16) PllIn {             // off-chain inputs of one sample
     float x;
@@ -481,7 +482,8 @@ struct __align__(16) PllIn {             // off-chain inputs of one sample
     double v;                            // w * trigOffset after this step (:166-167)
     int vi16;                            // 16 * rint(v/ulp) for the binade the slot was prepared in (16 * : see pll_table_group) ...
     float vr;                            // ... and fl32(v/ulp - vi), |vr| <= 0.5
-    int pad[2];
+    float c;                             // pi*(x < 0) - (w*trigOffset before this step mod 2 pi): the predictor's errorD is wrap(c - phaseEst)
+    int pad;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -527,7 +529,7 @@ struct TableRun {
     float inv_ulp_f, pi_f;           // 1/ulp (a power of two); rint(phaseEst/ulp) at the group start
     int cu_base16;                   // 16 * the same rint as an integer
     int base, cnt;                   // first step and number of steps of the group
-    unsigned in_base, tab_base, sg_base, sph_base;   // shared-window addresses: ring {vi, vr}, tables, parked indices, phaseEst records
+    unsigned in_base, tab_base, sg_base, prog_addr;   // shared-window addresses: ring {vi16, vr}, tables, parked indices, progress word
     int gi;                          // in: grid index of the trigArg before the group; out: of the last one
     int n_exact;                     // out: blocks of 16 that had to be stepped the exact way
     int fatal;                       // out: a block could not be completed here; the caller redoes the group
@@ -538,13 +540,14 @@ struct TableRun {
     float toff_base;                 // trigOffset before the group
 };
 
-// A block of up to 16 steps the exact way (the single-warp speculative step: sincos of the
-// known trigArg on the chain, ~300 cycles per step), from the state before the block:
-// the fall-back for a block in which a table was late, the grid point lay outside its
-// table, a candidate's guard failed or the grid index was too close to a tie.  Publishes
-// phaseEst and parks the grid indices exactly as the table steps do, and hands back
-// Kp*errorD, Ki*errorD of the sample after the block so that the table steps resume.
-// Returns false if one of ITS guards fails (the caller then redoes the whole group).
+// A block of up to 16 steps the exact way (the checked single-warp step: sincos of the
+// known trigArg on the chain, ~300 cycles per step; the reference's statements one by one
+// where a guard of that fails), from the state before the block: the fall-back for a
+// block in which a table was late, the grid point lay outside its table, a candidate's
+// guard failed or the grid index was too close to a tie.  Parks the grid indices exactly
+// as the table steps do, and hands back Kp*errorD, Ki*errorD of the sample after the
+// block so that the table steps resume.  Returns false if trigArg left the binade the
+// group's grid belongs to (the caller then redoes the whole group).
 __device__ __noinline__ bool pll_block_exact(TableRun &r, int u0, int nsteps, const int lane)
 {
     using namespace pllcore;
@@ -553,14 +556,13 @@ __device__ __noinline__ bool pll_block_exact(TableRun &r, int u0, int nsteps, co
     Chain c;
     c.integ = r.integ;
     c.ph = r.ph;
-    c.toff = r.toff_base + (float)(u0 - r.base);     // only ever incremented here; v comes from the ring
+    c.toff = fminf(r.toff_base + (float)(u0 - r.base), 16777216.0f);   // the counter saturates (:166)
     c.tad = p_mul((double)gi, r.ulp);
     c.fi = c.fq = 0.0f;
     chain_refresh(c);
-    if (c.binade == FMRX_DISARMED || c.ulp != r.ulp)
-        return false;
-    bool ok = true;
     for (int j = 0; j < nsteps; j++) {
+        if (c.binade == FMRX_DISARMED || c.ulp != r.ulp)
+            return false;
         const int u = u0 + j;
         const PllIn i = r.ring[u & (PLL_RING - 1)];
         StepIn in;
@@ -569,27 +571,71 @@ __device__ __noinline__ bool pll_block_exact(TableRun &r, int u0, int nsteps, co
         in.inv_x = i.inv_x;
         in.turn = i2d(i.turn_hi, 0);
         in.v = i.v;
-        ok &= chain_step_spec(c, r.k, K, in);
+        if (!chain_step_fast(c, r.k, K, in))
+            chain_step_generic(c, r.k, i.x);
         const int g = grid_index(grid_round(c.tad, c.inv_ulp));
-        if (lane == 0) {
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(r.sg_base + 4u * (unsigned)(u - r.base)), "r"(g) : "memory");
-            if ((u & 1) == 0)
-                asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(r.sph_base + (unsigned)(u & (PLL_TABLES - 1)) * 8u),
-                             "r"(__float_as_int(c.ph)), "r"(u + 1)
-                             : "memory");
-        }
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(r.sg_base + 4u * (unsigned)(u - r.base)), "r"(g));
         gi = g;
     }
+    if (c.binade == FMRX_DISARMED || c.ulp != r.ulp)
+        return false;
     // Kp*errorD, Ki*errorD of the sample after the block, from the now known trigArg
     const PllIn nx = r.ring[(u0 + nsteps) & (PLL_RING - 1)];
     const Feedback f = make_feedback(K, c.tad, i2d(nx.turn_hi, 0), nx.inv_x, nullptr, nullptr);
-    const float ed = error_from_feedback(f, nx.x, nx.xd, ok);
+    bool ok = true;
+    float ed = error_from_feedback(f, nx.x, nx.xd, ok);
+    if (!ok) {           // the shortcut's guard: the reference's own atan2 of its own float products
+        float fi, fq;
+        chain_feedback(c, fi, fq);
+        ed = p_d2f(atan2((double)p_fmulf(nx.x, -fq), (double)p_fmulf(nx.x, fi)));
+    }
     r.kpe = p_fmulf(r.k.kp, ed);
     r.kie = p_fmulf(r.k.ki, ed);
     r.integ = c.integ;
     r.ph = c.ph;
     r.gi = gi;
-    return ok;
+    return true;
+}
+
+// A group without tables, in blocks of 16 from a checkpoint: the single-warp speculative
+// step (sincos of the known trigArg on the chain, ~300 cycles) with the prepared inputs;
+// a block in which one of its guards fails -- or during which the fast step is disarmed
+// (irregular trigOffset, trigArg beyond the exact-reduction range) -- is stepped again
+// with the checked step, which falls back to the reference's statements one by one.
+// Parks the float trigArg of every step.
+__device__ __noinline__ void pll_group_checked(pllcore::Chain &chain, const pllcore::Consts k, const PllIn *ring, int base, int cnt,
+                                               bool regular, unsigned sg_base)
+{
+    using namespace pllcore;
+    const TrigK K = trig_constants();
+    Chain ch = chain;
+    for (int tb = 0; tb < cnt; tb += 16) {
+        const int nb = min(16, cnt - tb);
+        const Chain ckb = ch;
+        bool okb = regular && ch.binade != FMRX_DISARMED;
+        if (okb) {
+            for (int t = tb; t < tb + nb; t++) {
+                const PllIn i = ring[(base + t) & (PLL_RING - 1)];
+                StepIn in;
+                in.x = i.x;
+                in.xd = i.xd;
+                in.inv_x = i.inv_x;
+                in.turn = i2d(i.turn_hi, 0);
+                in.v = i.v;
+                okb &= chain_step_spec(ch, k, K, in);
+                // (no "memory" clobber: nothing here reads s_g, and the next sample's inputs may be loaded early)
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)t), "r"(__float_as_int(__double2float_rn(ch.tad))));
+            }
+        }
+        if (!okb) {
+            ch = ckb;
+            for (int t = tb; t < tb + nb; t++) {
+                const float ta = chain_step(ch, k, K, ring[(base + t) & (PLL_RING - 1)].x, nullptr);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)t), "r"(__float_as_int(ta)) : "memory");
+            }
+        }
+    }
+    chain = ch;
 }
 
 template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
@@ -598,11 +644,11 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
     float integ = r.integ, ph = r.ph, kpe = r.kpe, kie = r.kie;
     const float inv_ulp_f = r.inv_ulp_f, pi_f = r.pi_f;
     const int cu_base16 = r.cu_base16, base = r.base, cnt = r.cnt;
-    const unsigned in_base = r.in_base, tab_base = r.tab_base, sg_base = r.sg_base, sph_base = r.sph_base;
+    const unsigned in_base = r.in_base, tab_base = r.tab_base, sg_base = r.sg_base, prog_addr = r.prog_addr;
     int bad = 0, gi = r.gi, n_exact = 0;
     float worst = 0.0f;
-    // one step; vg = {vi, vr} of the sample, tab_a = address of its table row, sph_a = of its phaseEst record
-    auto step = [&](int u, unsigned tab_a, int2 vg, bool publish, unsigned sph_a) {
+    // one step; vg = {16*vi, vr} of the sample, tab_a = address of its table row
+    auto step = [&](int u, unsigned tab_a, int2 vg) {
         integ = p_faddf(integ, kie);                                  // :163
         ph = p_faddf(ph, p_faddf(kpe, integ));                       // :164
         const float tt = __fmaf_rn(ph, inv_ulp_f, -pi_f);
@@ -622,11 +668,6 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
         bad |= (e.z ^ gi) | (e.w ^ (u + 1));
         const float frac = p_faddf(z, -p_faddf(zm, -12582912.0f));
         worst = fmaxf(worst, __fmaf_rn(fmaxf(fabsf(tt), 4.0f), 0x1p-22f, fabsf(frac)));
-        // off the chain, every 2nd step: publish phaseEst(u) for later candidate tables.  (All
-        // lanes store the same record to the same address: one wavefront, and no branch or
-        // predicate on the chain.)
-        if (publish)
-            asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(sph_a), "r"(__float_as_int(ph)), "r"(u + 1) : "memory");
     };
     auto load_vg = [&](unsigned addr) {
         int2 v;
@@ -665,14 +706,13 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
         // of 16 and u0 is one): addresses are base + constant
         const unsigned in_a0 = in_base + (unsigned)(u0 & (PLL_RING - 1)) * (unsigned)sizeof(PllIn);
         const unsigned tab_a0 = tab_base + (unsigned)(u0 & (PLL_TABLES - 1)) * (16u * PLL_CANDS);
-        const unsigned sph_a0 = sph_base + (unsigned)(u0 & (PLL_TABLES - 1)) * 8u;
         const int2 vg_next_block = load_vg(in_base + (unsigned)((u0 + 16) & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
         int gis[16];
         int2 vg = vg0;
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             const int2 vg_n = (j < 15) ? load_vg(in_a0 + (unsigned)(j + 1) * (unsigned)sizeof(PllIn)) : vg_next_block;
-            step(u0 + j, tab_a0 + (unsigned)j * (16u * PLL_CANDS), vg, (j & 1) == 0, sph_a0 + (unsigned)j * 8u);
+            step(u0 + j, tab_a0 + (unsigned)j * (16u * PLL_CANDS), vg);
             gis[j] = gi;
             vg = vg_n;
         }
@@ -683,10 +723,12 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(gis[j]), "r"(gis[j + 1]),
                          "r"(gis[j + 2]), "r"(gis[j + 3])
                          : "memory");
-        if (!settle(u0, 16, integ0, ph0, gi0)) {
-            fatal = true;
+        if (!settle(u0, 16, integ0, ph0, gi0) || n_exact > PLL_EXACT_MAX) {
+            fatal = true;            // (more exact blocks than a group without tables costs: give the group up)
             break;
         }
+        // progress: lets the candidate warps reuse the table rows of this block, the predictor run on
+        asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(prog_addr), "r"(u0 + 16) : "memory");
     }
     if (!fatal && t < cnt) {     // the short last block of a launch
         const int u0 = base + t, nb = cnt - t;
@@ -695,8 +737,7 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
         for (int j = 0; j < nb; j++) {
             const int u = u0 + j;
             const int2 vg = load_vg(in_base + (unsigned)(u & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
-            step(u, tab_base + (unsigned)(u & (PLL_TABLES - 1)) * (16u * PLL_CANDS), vg, (u & 1) == 0,
-                 sph_base + (unsigned)(u & (PLL_TABLES - 1)) * 8u);
+            step(u, tab_base + (unsigned)(u & (PLL_TABLES - 1)) * (16u * PLL_CANDS), vg);
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(gi) : "memory");
         }
         fatal = !settle(u0, nb, integ0, ph0, gi0);
@@ -715,16 +756,18 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     using namespace pllcore;
     extern __shared__ __align__(16) unsigned char pll_dyn_smem[];
     PllIn *s_in = reinterpret_cast<PllIn *>(pll_dyn_smem);      // [PLL_RING]
-    __shared__ int2 s_ph[PLL_TABLES];                 // {phaseEst, step + 1} published by warp 0; {-, PLL_ABANDONED + g}: group g given up
-    // candidate tables, indexed by (step & 15, grid index & 31): {Kp*errorD, Ki*errorD of the next
+    __shared__ __align__(16) int2 s_ph[PLL_PH_RING];  // {predicted phaseEst, step + 1}, written by the predictor warp
+    __shared__ float s_hdr[2];                        // integrator, phaseEst at the start of the group (warp 0 -> predictor)
+    __shared__ int s_prog;                            // steps of the capture warp 0 has completed (per block of 16), or PLL_ABANDONED
+    // candidate tables, indexed by (step & 63, grid index & 15): {Kp*errorD, Ki*errorD of the next
     // sample, grid index, step+1 (negated if a guard failed)}; one self-validating 16-byte record per lane
-    __shared__ int4 s_tab[PLL_TABLES][PLL_CANDS];
+    __shared__ __align__(16 * PLL_CANDS) int4 s_tab[PLL_TABLES][PLL_CANDS];   // row-aligned: warp 0 ORs the entry offset into the row address
     __shared__ __align__(16) int s_g[2][PLL_GROUP];                 // grid index of each trigArg of the group, double-buffered
     __shared__ double s_grid[2];                      // ulp, 1/ulp of the current group
     __shared__ double s_prep_ulp[4];                  // ulp the ring slots of each group were prepared with
     __shared__ double s_ulp_hist[2];                  // ulp the parked grid indices of a group refer to
     __shared__ int s_spec[2];                         // 1: s_g holds grid indices, 0: float bit patterns
-    __shared__ int s_flag[4];                         // [0] group runs speculatively, [1] error
+    __shared__ int s_flag[4];                         // [0] group runs speculatively, [1] error, [2] the next group's slots are stale
 
     const int c = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -743,9 +786,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     const float toff0 = st[5];
     const bool regular = toff_is_regular(toff0);
     const int t0 = regular ? (int)toff0 : 0;
-    // roles by scheduler (warp & 3): 0 = the chain (warp 0; warps 4, 8 idle), 1 = I/O, 2 and 3 = candidates
+    // roles by scheduler (warp & 3): 0 = the chain (warp 0; warps 4, 8 idle), 1 = I/O and the predictor, 2 and 3 = candidates
     const int role = warp & 3;
-    const int io_id = warp >> 2;                          // 0..2 for warps 1, 5, 9
+    const int io_id = warp >> 2;                          // 0, 1 for warps 1, 5 (2: warp 9, the predictor)
     const int cand_id = (warp >> 2) * 2 + role - 2;       // 0..5 for warps 2, 3, 6, 7, 10, 11
 
     // I/O warp: one lane per sample, off-chain inputs of the samples of a group into the ring
@@ -764,14 +807,15 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             const double qv = grid_round(in.v, s_grid[1]);
             in.vi16 = grid_index(qv) << 4;
             in.vr = __double2float_rn(__fma_rn(in.v, s_grid[1], -p_add(qv, -FMRX_RINT_MAGIC)));
-            in.pad[0] = in.pad[1] = 0;
+            in.c = predictor_c(k, pvv, (float)min(t0 + u, 16777216));      // trigOffset BEFORE this step
+            in.pad = 0;
             s_in[u & (PLL_RING - 1)] = in;
         }
         if (lane == 0 && io_id == 0)
             s_prep_ulp[(base / PLL_GROUP) & 3] = s_grid[0];
     };
 
-    if (threadIdx.x < PLL_TABLES)
+    if (threadIdx.x < PLL_PH_RING)
         s_ph[threadIdx.x] = make_int2(0, 0);
     for (int i = threadIdx.x; i < PLL_TABLES * PLL_CANDS; i += PLL_THREADS)
         s_tab[i / PLL_CANDS][i % PLL_CANDS] = make_int4(0, 0, 0, (int)0x80000000);
@@ -802,7 +846,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         }
     }
     __syncthreads();
-    if (role == 1) {
+    if (role == 1 && io_id < PLL_IO_WARPS) {
         prepare(0);
         prepare(PLL_GROUP);
     }
@@ -814,15 +858,16 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         // ---- group header (warp 0) ----
         if (warp == 0) {
             ck = ch;
-            const bool spec = regular && !dead && skip == 0 && ch.binade != FMRX_DISARMED &&
+            const bool spec = !(a.variant & 512) && regular && !dead && skip == 0 && ch.binade != FMRX_DISARMED &&
                               s_prep_ulp[g & 3] == ch.ulp;
             if (lane == 0) {
                 s_flag[0] = spec;
                 s_grid[0] = ch.ulp;
                 s_grid[1] = ch.inv_ulp;
-                // phaseEst "of steps base-L .. base-1" for the first candidate tables
-                for (int j = 1; j <= PLL_LOOKBACK; j++)
-                    s_ph[(base - j) & (PLL_TABLES - 1)] = make_int2(__float_as_int(ch.ph), base - j + 1);
+                s_flag[2] = s_prep_ulp[(g + 1) & 3] != ch.ulp;
+                s_hdr[0] = ch.integ;
+                s_hdr[1] = ch.ph;
+                s_prog = base;
             }
         }
         __syncthreads();
@@ -861,7 +906,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 dbg_pre += dbg_w0 - dbg_ga;
                 {   // lane t watches table t
                     const int want = base + lane + 1;
-                    const bool need = lane < PLL_LOOKBACK && lane < cnt;
+                    const bool need = lane < 16 && lane < cnt;           // the first block's tables
                     int spin = 0;
                     for (;;) {
                         const int z = ld_v4(&s_tab[(base + lane) & (PLL_TABLES - 1)][0]).w;
@@ -892,7 +937,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 r.in_base = smem_u32(&s_in[0]) + 32u;                            // offset of {vi, vr} in a slot
                 r.tab_base = smem_u32(&s_tab[0][0]);
                 r.sg_base = smem_u32(&s_g[g & 1][0]);
-                r.sph_base = smem_u32(&s_ph[0]);
+                r.prog_addr = smem_u32(&s_prog);
                 r.gi = __double2int_rn(p_mul(ch.tad, inv_ulp));                  // exact: trigArg is on the grid
                 r.n_exact = 0;
                 r.fatal = 0;
@@ -903,10 +948,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 if (good) {
                     __syncwarp();
                     const long long c0 = clock64();
-                    if ((a.variant & 255) == 1)
-                        pll_table_group<1>(r, lane);
-                    else
-                        pll_table_group<0>(r, lane);
+                    pll_table_group<0>(r, lane);
                     const long long c1 = clock64();
                     dbg_cyc += c1 - c0;
                     dbg_steps += cnt;
@@ -922,20 +964,13 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     have_ed = true;
                     kpe_next = r.kpe;
                     kie_next = r.kie;
-                    // a group that needed many exact blocks is no faster than a checked one:
-                    // back off like after a failure, but keep its (exact) result
-                    if (r.n_exact > PLL_EXACT_MAX) {
-                        backoff = min(backoff ? 2 * backoff : 1, PLL_BACKOFF_MAX);
-                        skip = backoff;
-                    } else {
-                        backoff = 0;
-                    }
+                    backoff = 0;
                 }
             }
             if (!good) {
                 if (spec) {
-                    // the candidate warps stop polling for this group: every phaseEst slot says so
-                    asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(smem_u32(&s_ph[lane])), "r"(0), "r"(PLL_ABANDONED + g) : "memory");
+                    // the predictor and the candidate warps stop working on this group
+                    asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(smem_u32(&s_prog)), "r"(PLL_ABANDONED) : "memory");
                     n_redone++;
                     backoff = min(backoff ? 2 * backoff : 1, PLL_BACKOFF_MAX);
                     skip = backoff - 1;
@@ -947,33 +982,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     chain_refresh(ch);
                     stale = false;
                 }
-                // second line: the single-warp speculative step (sequential make_feedback on the
-                // chain, ~300 cycles per step) over the whole group from a checkpoint ...
-                const Chain ck2 = ch;
-                bool ok2 = regular && ch.binade != FMRX_DISARMED;
-                if (ok2) {
-                    for (int t = 0; t < cnt; t++) {
-                        const PllIn i = s_in[(base + t) & (PLL_RING - 1)];
-                        StepIn in;
-                        in.x = i.x;
-                        in.xd = i.xd;
-                        in.inv_x = i.inv_x;
-                        in.turn = i2d(i.turn_hi, 0);
-                        in.v = i.v;
-                        ok2 &= chain_step_spec(ch, k, K, in);
-                        if (lane == 0)
-                            s_g[g & 1][t] = __float_as_int(__double2float_rn(ch.tad));
-                    }
-                }
-                // ... and if one of ITS guards failed too, the checked/generic step, one by one
-                if (!ok2) {
-                    ch = ck2;
-                    for (int t = 0; t < cnt; t++) {
-                        const float ta = chain_step(ch, k, K, s_in[(base + t) & (PLL_RING - 1)].x, nullptr);
-                        if (lane == 0)
-                            s_g[g & 1][t] = __float_as_int(ta);          // checked groups park the float itself
-                    }
-                }
+                // the group without tables (a separately compiled function, like the table steps)
+                pll_group_checked(ch, k, s_in, base, cnt, regular, smem_u32(&s_g[g & 1][0]));
                 have_ed = false;
             }
             if (lane == 0) {
@@ -983,32 +993,46 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         } else if (role >= 2) {
             // ================= candidate tables =================
             // A warp evaluates two consecutive steps at once, one per half-warp (16 grid points
-            // each): steps base + 2*cand_id + {0, 1} (mod 2*PLL_CAND_WARPS).  Both need the same
-            // phaseEst record (every 4th step is published and the first of the two is even).
+            // each): steps base + 2*cand_id + {0, 1} (mod 2*PLL_CAND_WARPS), each centred on the
+            // predictor's phaseEst for that very step.
             if (spec) {
                 const int half = lane >> 4, hl = lane & (PLL_CANDS - 1);
+                const unsigned prog_a = smem_u32(&s_prog);
+                auto progress = [&]() {
+                    int v;
+                    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(prog_a) : "memory");
+                    return v;
+                };
                 for (int t2 = 2 * cand_id; t2 < cnt; t2 += 2 * PLL_CAND_WARPS) {
                     const bool live = t2 + half < cnt;
-                    const int u = base + t2 + (live ? half : 0);
+                    const int ue = base + t2;                            // the even step of the pair
+                    const int u = ue + (live ? half : 0);
                     const double v = s_in[u & (PLL_RING - 1)].v;
                     const PllIn nx = s_in[(u + 1) & (PLL_RING - 1)];     // the sample the result is for
-                    const int ur = base + t2 - PLL_LOOKBACK;             // even: published
-                    // poll while the slot still holds an older record
-                    const long long dbg_q0 = clock64();
-                    int2 pr = ld_v2(&s_ph[ur & (PLL_TABLES - 1)]);
-                    for (int spin = 0; pr.y - (ur + 1) < 0 && spin < PLL_SPIN_LIMIT; spin++)
-                        pr = ld_v2(&s_ph[ur & (PLL_TABLES - 1)]);
-
-                    if (pr.y >= PLL_ABANDONED)       // warp 0 gave the group up
+                    // the predictor publishes in order: once the later record of the pair is there, both are
+                    const int last = min(ue + 1, base + cnt - 1);
+                    int4 pr;
+                    int prog = 0, spin = 0;
+                    for (;; spin++) {
+                        pr = ld_v4(&s_ph[ue & (PLL_PH_RING - 1)]);       // {phaseEst(ue), ue + 1, phaseEst(ue + 1), ue + 2}
+                        const int seq = (last == ue) ? pr.y : pr.w;
+                        if (seq - (last + 1) >= 0 || spin >= PLL_SPIN_LIMIT)
+                            break;
+                        if ((spin & 7) == 7 && (prog = progress()) == PLL_ABANDONED)
+                            break;
+                    }
+                    if (prog == PLL_ABANDONED)
                         break;
-                    if (pr.y - (ur + 1) > 0)         // this warp fell a whole ring behind and the record is gone: skip the
-                        continue;                    // pair (warp 0 steps that block the exact way) rather than wait for ever
-                    if (pr.y != ur + 1) {
-                        s_flag[1] = 1;               // gave up: warp 0 will see missing tables
-                        break;
+                    if (pr.y != ue + 1) {            // timed out, or this warp fell a whole ring behind: no table
+                        if (spin >= PLL_SPIN_LIMIT) {
+                            s_flag[1] = 1;
+                            break;
+                        }
+                        continue;
                     }
                     // this lane's grid point: the one congruent to `hl` (mod 16) in [G_c-8, G_c+7]
-                    const int gc = grid_index(grid_round(p_add(v, (double)__int_as_float(pr.x)), inv_ulp));
+                    const float php = __int_as_float(half ? pr.z : pr.x);
+                    const int gc = grid_index(grid_round(p_add(v, (double)php), inv_ulp));
                     const int gl = gc - PLL_CANDS / 2 + ((hl - (gc - PLL_CANDS / 2)) & (PLL_CANDS - 1));
                     const double tad = p_mul((double)gl, ulp);                        // exact
                     const Feedback f = make_feedback(K, tad, i2d(nx.turn_hi, 0), nx.inv_x, nullptr, nullptr);
@@ -1016,15 +1040,63 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const int ag = gl < 0 ? -gl : gl;
                     bool ok = ag > (1 << 23) && ag < (1 << 24);
                     const float ed = error_from_feedback(f, nx.x, nx.xd, ok);         // :159-161 of sample u+1
-                    if (t2 < 12) { dbg_pre += dbg_q0 - dbg_ga; dbg_wait += clock64() - dbg_q0; }
-                    else if (t2 < 24) { dbg_cyc += clock64() - dbg_q0; dbg_steps++; }
+                    // the rows still hold the tables of steps ue - 64, ue - 63: wait until warp 0 is past them
+                    for (spin = 0; (prog = progress()) != PLL_ABANDONED && prog - (ue + 2 - PLL_TABLES) < 0 && spin < PLL_SPIN_LIMIT; spin++)
+                        ;
+                    if (prog == PLL_ABANDONED)
+                        break;
+                    if (spin >= PLL_SPIN_LIMIT) {
+                        s_flag[1] = 1;
+                        break;
+                    }
                     if (live)
                         st_v4(&s_tab[u & (PLL_TABLES - 1)][hl], __float_as_int(p_fmulf(k.kp, ed)), __float_as_int(p_fmulf(k.ki, ed)), gl,
                               ok ? u + 1 : -(u + 1));
                 }
             }
-        } else if (role == 1) {
+        } else if (warp == PLL_PRED_WARP) {
+            // ================= the run-ahead predictor =================
+            // The same recurrence with the phase detector replaced by what it computes up to
+            // rounding (fmrx_pll_core.h, predictor_step): nine dependent float operations per
+            // step, so it runs about twice as fast as warp 0 can consume tables, and its phaseEst
+            // stays within a grid step or two of the exact one for the whole group (it restarts
+            // from the exact state at every group).  It is only ever used to CENTRE the tables.
+            if (spec) {
+                float integ = s_hdr[0], ph = s_hdr[1];
+                const unsigned prog_a = smem_u32(&s_prog);
+                const unsigned ph_a = smem_u32(&s_ph[0]);
+                const unsigned c_a = smem_u32(&s_in[0]) + 40u;                   // offset of c in a slot
+                int prog = base;
+                for (int t = 0; t < cnt; t += 16) {
+                    const int u0 = base + t;
+                    int spin = 0;                // stay within PLL_PRED_LEAD of warp 0
+                    do {
+                        asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(prog) : "r"(prog_a) : "memory");
+                    } while (prog != PLL_ABANDONED && u0 - prog > PLL_PRED_LEAD - 16 && ++spin < PLL_SPIN_LIMIT);
+                    if (prog == PLL_ABANDONED || spin >= PLL_SPIN_LIMIT)
+                        break;
+                    // the 16 c's of the block first (they do not wrap inside it), then the dependent steps
+                    const unsigned c_a0 = c_a + (unsigned)(u0 & (PLL_RING - 1)) * (unsigned)sizeof(PllIn);
+                    const unsigned ph_a0 = ph_a + (unsigned)(u0 & (PLL_PH_RING - 1)) * 8u;
+                    float cs[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=f"(cs[j]) : "r"(c_a0 + (unsigned)j * (unsigned)sizeof(PllIn)));
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        predictor_step(k, cs[j], integ, ph);         // steps past the end of a short last block are never used
+                        asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(ph_a0 + (unsigned)j * 8u), "r"(__float_as_int(ph)),
+                                     "r"(u0 + j + 1)
+                                     : "memory");
+                    }
+                }
+            }
+        } else if (role == 1 && io_id < PLL_IO_WARPS) {
             // ================= I/O =================
+            // (a binade change strands the two groups prepared ahead with the old grid: the next one
+            // is prepared again here, so that only the group running now goes without tables)
+            if (s_flag[2])
+                prepare(base + PLL_GROUP);
             prepare(base + 2 * PLL_GROUP);
             if (g > 0) {                     // previous group: always complete
                 const int pb = base - PLL_GROUP;

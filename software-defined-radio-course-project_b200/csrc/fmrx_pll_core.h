@@ -61,6 +61,7 @@ FMRX_HD double p_mul(double a, double b) { return __dmul_rn(a, b); }
 FMRX_HD double p_add(double a, double b) { return __dadd_rn(a, b); }
 FMRX_HD float p_fmulf(float a, float b) { return __fmul_rn(a, b); }
 FMRX_HD float p_faddf(float a, float b) { return __fadd_rn(a, b); }
+FMRX_HD float p_fmaf(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 FMRX_HD float p_d2f(double a) { return __double2float_rn(a); }
 FMRX_HD int p_hi32(double a) { return __double2hiint(a); }
 #else
@@ -70,6 +71,7 @@ FMRX_HD double p_mul(double a, double b) { return a * b; }
 FMRX_HD double p_add(double a, double b) { return a + b; }
 FMRX_HD float p_fmulf(float a, float b) { return a * b; }
 FMRX_HD float p_faddf(float a, float b) { return a + b; }
+FMRX_HD float p_fmaf(float a, float b, float c) { return fmaf(a, b, c); }
 FMRX_HD float p_d2f(double a) { return (float)a; }
 FMRX_HD int p_hi32(double a)
 {
@@ -443,6 +445,36 @@ FMRX_HD float chain_step(Chain &c, const Consts &k, const TrigK &K, float x, uns
             ++*slow;
     }
     return p_d2f(c.tad);
+}
+
+// ---- the run-ahead predictor ------------------------------------------------------------
+//
+// The phase detector (:159-161) computes atan2(x*(-sin t), x*cos t) with t the previous
+// trigArg: up to the float roundings of the feedback pair and of the two products that is
+// wrap(pi*(x < 0) - t) onto (-pi, pi].  With t = w*trigOffset + phaseEst, the part that
+// does not depend on the recurrence,
+//     c = pi*(x < 0) - (w*trigOffset mod 2 pi),
+// is prepared per sample, and one predictor step is five float operations for the phase
+// detector plus the reference's own four for the loop filter.  The predictor is never
+// used for a result: it only says where to CENTRE the candidate table of a step, and it
+// restarts from the exact (integrator, phaseEst) at every group.  While the loop is
+// locked its phaseEst stays within a grid step of the exact one over a group
+// (tests/test_pll_model.py::test_predictor_tracks_the_exact_recurrence).
+FMRX_HD float predictor_c(const Consts &k, float x, float toff_before)
+{
+    const double vp = p_mul(k.w, (double)toff_before);
+    const double kq = p_add(p_add(p_mul(vp, 0.15915494309189535), FMRX_RINT_MAGIC), -FMRX_RINT_MAGIC);
+    const double rp = p_fma(-kq, 2.4492935982947064e-16, p_fma(-kq, 6.283185307179586, vp));   // vp mod 2 pi, in [-pi, pi]
+    return p_d2f(p_add(x < 0.0f ? 3.141592653589793 : 0.0, -rp));
+}
+
+FMRX_HD void predictor_step(const Consts &k, float c, float &integ, float &ph)
+{
+    const float d = p_faddf(c, -ph);
+    const float kq = p_faddf(p_faddf(p_fmulf(d, 0.15915494f), 12582912.0f), -12582912.0f);   // rint(d / 2 pi)
+    const float e = p_fmaf(-kq, 6.2831855f, d);
+    integ = p_faddf(integ, p_fmulf(k.ki, e));                        // :163
+    ph = p_faddf(ph, p_faddf(p_fmulf(k.kp, e), integ));              // :164
 }
 
 // trigOffset advances by float additions of 1 (:166).  From an integer-valued start

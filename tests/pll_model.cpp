@@ -76,6 +76,46 @@ void pll_model_sincos_d(const float *x, int n, double *s, double *c)
     }
 }
 
+
+// The run-ahead predictor against the exact recurrence: from the exact state at the start
+// of each group of `group` samples, step the predictor and the exact chain side by side
+// and record, per group, the largest distance (in float grid steps of trigArg) between the
+// exact trigArg and the grid point the predictor would centre the candidate table on.
+// state5 as in pll_model_run; worst[n_groups].
+int pll_model_predict(const float *pilot, int n, float freq, float Fs, float bw, float *state5, int group, int *worst)
+{
+    Consts k;
+    k.kp = bw * 2.666f;
+    k.ki = (bw * bw) * 3.555f;
+    k.w = (2.0 * 3.14159265358979323846) * (double)(freq / Fs);
+    const TrigK K = trig_constants();
+    Chain c;
+    memset(&c, 0, sizeof(c));
+    c.integ = state5[0]; c.ph = state5[1]; c.fi = state5[2]; c.fq = state5[3]; c.toff = state5[4];
+    chain_load(c, k);
+    int ng = 0;
+    for (int b = 0; b < n; b += group, ng++) {
+        float pi = c.integ, pp = c.ph;          // the predictor restarts from the exact state
+        int w = 0;
+        for (int j = 0; j < group && b + j < n; j++) {
+            const float x = pilot[b + j];
+            predictor_step(k, predictor_c(k, x, c.toff), pi, pp);
+            const float ta = chain_step(c, k, K, x, nullptr);
+            const double v = k.w * (double)c.toff;      // trigOffset after the step
+            int e;
+            (void)frexpf(fabsf(ta), &e);
+            const double ulp = ldexp(1.0, e - 1 - 23);
+            const double d = fabs((double)ta / ulp - nearbyint((v + (double)pp) / ulp));
+            if (ta != 0.0f && d > w)
+                w = d > 1e9 ? 1000000000 : (int)d;
+        }
+        worst[ng] = w;
+    }
+    state5[0] = c.integ; state5[1] = c.ph; state5[4] = c.toff;
+    chain_feedback(c, state5[2], state5[3]);
+    return ng;
+}
+
 }  // extern "C"
 
 // feedbackI/Q implied by (phaseEst, trigOffset): fl32(cos, sin)(fl32(w*toff + ph))

@@ -98,3 +98,26 @@ def test_fast_pll_other_loop_parameters(model, port):
     trig, st, _ = run_model(model, x, 114000.0, 240e3, st6[[0, 1, 2, 3, 5]])
     assert_bits_equal(trig, otrig, "trigArg beyond 2^24")
     assert_bits_equal(st, ost[[0, 1, 2, 3, 5]], "state beyond 2^24")
+
+
+@pytest.mark.parametrize("mode,seed,pilot_hz", [(0, 0, 19000.0), (0, 3, 19001.5), (1, 2, 19000.0)])
+def test_predictor_tracks_the_exact_recurrence(model, port, synth, mode, seed, pilot_hz):
+    """k_pll centres each step's candidate table (16 grid points, [G-8, G+7]) on the run-ahead
+    predictor's phaseEst (csrc/fmrx_pll_core.h predictor_step), restarted from the exact state
+    every 1024 steps.  On a locked loop the exact trigArg must stay within two grid steps of
+    that centre for every group after the first (where trigArg starts at 0 and the float grid
+    is arbitrarily fine)."""
+    info = port.mode(mode, 51)
+    nb = int(3.0 * info.rf_fs * 2 / info.block_size)
+    iq = synth.synth_iq(nb * info.block_size // 2, info.rf_fs, seed=seed, pilot_hz=pilot_hz)
+    _, st = port.chain(mode, 51).run(iq, stages=("pilot",))
+    pilot = st["pilot"]
+    group = 1024
+    worst = np.zeros((len(pilot) + group - 1) // group, np.int32)
+    state = np.array([0.0, 0.0, 1.0, 0.0, 0.0], np.float32)
+    model.pll_model_predict.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, f32p, C.c_int,
+                                        C.POINTER(C.c_int)]
+    ng = model.pll_model_predict(pilot.ctypes.data_as(f32p), len(pilot), 19000.0, float(info.if_fs), 0.01,
+                                 state.ctypes.data_as(f32p), group, worst.ctypes.data_as(C.POINTER(C.c_int)))
+    assert ng == len(worst)
+    assert worst[1:].max() <= 2, worst[:20]
