@@ -457,19 +457,20 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 
 constexpr int PLL_WARPS = 12;
 constexpr int PLL_THREADS = 32 * PLL_WARPS;
-constexpr int PLL_CAND_WARPS = 6;        // warps 2,3,6,7,10,11 (schedulers 2 and 3), two steps each: one per half-warp
-constexpr int PLL_CANDS = 16;            // grid points per candidate table
+constexpr int PLL_CAND_WARPS = 6;        // warps 2,3,6,7,10,11 (schedulers 2 and 3), eight steps each: one per quad of lanes
+constexpr int PLL_BATCH = 8;             // steps per pass of a candidate warp
+constexpr int PLL_ROW_INVALID = 0x40000000;   // centre key of a table none of warp 0's grid points can match (|grid index| < 2^24)
 constexpr int PLL_IO_WARPS = 2;          // warps 1, 5 (scheduler 1); warps 4 and 8 (warp 0's scheduler) only take part in the barriers
 constexpr int PLL_PRED_WARP = 9;         // the run-ahead predictor (scheduler 1)
 constexpr int PLL_GROUP = 1024;          // steps between checkpoints / barriers
 constexpr int PLL_RING = 4 * PLL_GROUP;  // per-sample input ring: 4 groups
 constexpr int kPllSpareSms = 32;         // SMs that must stay free for the FIR kernels before PLL CTAs claim whole SMs
-constexpr int PLL_TABLES = 64;           // candidate tables in flight (a ring over the steps)
+constexpr int PLL_TABLES = 128;          // candidate tables in flight (a ring over the steps)
 constexpr int PLL_PH_RING = 256;         // predicted-phaseEst records in flight
 constexpr int PLL_PRED_LEAD = 128;       // the predictor stays at most this far ahead of warp 0
 constexpr int PLL_SPIN_LIMIT = 1 << 16;  // bounded polling (~1 ms): a bug must not hang the GPU
-static_assert(PLL_CANDS == 16 && PLL_TABLES % 16 == 0 && PLL_PH_RING % 2 == 0, "two steps per candidate warp; no ring wraps inside a block of 16");
-static_assert(PLL_PRED_LEAD + 2 * PLL_TABLES <= PLL_PH_RING, "a record outlives every candidate that may still need it");
+static_assert(PLL_TABLES % 16 == 0 && PLL_PH_RING % PLL_BATCH == 0, "no ring wraps inside a block of 16 steps or a batch of candidates");
+static_assert(PLL_PRED_LEAD + PLL_TABLES <= PLL_PH_RING, "a record outlives every candidate that may still need it");
 constexpr int PLL_ABANDONED = -1;        // progress value: warp 0 gave the group up
 constexpr int PLL_EXACT_MAX = PLL_GROUP / 128;  // exact blocks (an eighth of the group) after which a speculated group is given up
 constexpr int PLL_BACKOFF_MAX = 64;      // groups run unspeculated between retries after repeated failures
@@ -480,7 +481,7 @@ struct __align__(16) PllIn {             // off-chain inputs of one sample
     double xd;                           // (double)x
     double inv_x;                        // 1/(double)x, IEEE divide
     double v;                            // w * trigOffset after this step (:166-167)
-    int vi16;                            // 16 * rint(v/ulp) for the binade the slot was prepared in (16 * : see pll_table_group) ...
+    int vi;                              // rint(v/ulp) for the binade the slot was prepared in ...
     float vr;                            // ... and fl32(v/ulp - vi), |vr| <= 0.5
     float c;                             // pi*(x < 0) - (w*trigOffset before this step mod 2 pi): the predictor's errorD is wrap(c - phaseEst)
     int pad;
@@ -527,9 +528,9 @@ __device__ __forceinline__ double i2d(int hi, int lo) { return __hiloint2double(
 struct TableRun {
     float integ, ph, kpe, kie;       // in/out: loop filter state; Kp*errorD, Ki*errorD of the sample about to run
     float inv_ulp_f, pi_f;           // 1/ulp (a power of two); rint(phaseEst/ulp) at the group start
-    int cu_base16;                   // 16 * the same rint as an integer
+    int kbase;                       // the same rint as an integer, less the bit pattern of 1.5 * 2^23: grid index = bits(zm) + vi + kbase
     int base, cnt;                   // first step and number of steps of the group
-    unsigned in_base, tab_base, sg_base, prog_addr;   // shared-window addresses: ring {vi16, vr}, tables, parked indices, progress word
+    unsigned in_base, tab_base, sg_base, prog_addr;   // shared-window addresses: ring {vi, vr}, tables, parked indices, progress word
     int gi;                          // in: grid index of the trigArg before the group; out: of the last one
     int n_exact;                     // out: blocks of 16 that had to be stepped the exact way
     int fatal;                       // out: a block could not be completed here; the caller redoes the group
@@ -638,40 +639,68 @@ __device__ __noinline__ void pll_group_checked(pllcore::Chain &chain, const pllc
     chain = ch;
 }
 
+// A candidate table: what the next sample's phase detector gives for the three float-grid
+// points around the predictor's trigArg of a step.  32 bytes, written by ONE store
+// instruction of a candidate warp (four lanes, 8 bytes each), read by warp 0 as two
+// 16-byte halves -- the half with the key and the block stamp FIRST, so that a half
+// overwritten in between can only fail the check, never pass it.
+struct __align__(32) PllRow {
+    float kpe0, kie0, kpe1, kie1;    // Kp*errorD, Ki*errorD of the next sample if trigArg is grid point keyC - 1, keyC
+    float kpe2, kie2;                // ... keyC + 1
+    int keyC;                        // the centre grid point (PLL_ROW_INVALID: a candidate's guard failed)
+    int stamp;                       // (step & ~15) + 1: which block of 16 steps of the launch the table is for
+};
+
 template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
 {
     using namespace pllcore;
     float integ = r.integ, ph = r.ph, kpe = r.kpe, kie = r.kie;
     const float inv_ulp_f = r.inv_ulp_f, pi_f = r.pi_f;
-    const int cu_base16 = r.cu_base16, base = r.base, cnt = r.cnt;
+    const int kbase = r.kbase, base = r.base, cnt = r.cnt;
     const unsigned in_base = r.in_base, tab_base = r.tab_base, sg_base = r.sg_base, prog_addr = r.prog_addr;
     int bad = 0, gi = r.gi, n_exact = 0;
     float worst = 0.0f;
-    // one step; vg = {16*vi, vr} of the sample, tab_a = address of its table row
-    auto step = [&](int u, unsigned tab_a, int2 vg) {
-        integ = p_faddf(integ, kie);                                  // :163
-        ph = p_faddf(ph, p_faddf(kpe, integ));                       // :164
+    // One step: from (integrator, phaseEst) after sample u, the table of step u and {vi, vr} of
+    // sample u to the state after sample u+1 -- or, with `last`, to Kp*errorD, Ki*errorD of sample
+    // u+1 (what a block hands to the next one and to the exact fall-back).
+    //   - three hypotheses: trigArg(u) is grid point keyC-1, keyC, keyC+1; for each the loop filter
+    //     (:163-164) of sample u+1 -- nine float additions that only need the state, not the index;
+    //   - the index (:166-167): zm = (fma(phaseEst, 1/ulp, -pi) + vr) + 1.5*2^23 holds the grid index
+    //     less (vi + pi) in its low bits, so hypothesis j is right iff zm == the float whose bits are
+    //     keyC + j - 1 - (vi + kbase): three float compares against values ready long before;
+    //   - two predicated moves pick the state.  On the dependent chain: FFMA, FADD, FADD, compare,
+    //     move -- the three additions of the loop filter run beside it.
+    auto step = [&](int4 ra, int4 rb, int2 vg, int stamp, bool last) {
+        const float kpe0 = __int_as_float(ra.x), kie0 = __int_as_float(ra.y), kpe1 = __int_as_float(ra.z), kie1 = __int_as_float(ra.w);
+        const float kpe2 = __int_as_float(rb.x), kie2 = __int_as_float(rb.y);
         const float tt = __fmaf_rn(ph, inv_ulp_f, -pi_f);
         const float z = p_faddf(tt, __int_as_float(vg.y));
         const float zm = p_faddf(z, 12582912.0f);                     // 1.5 * 2^23: rint in the low bits
-        // 16 * (vi + pi) is ready long before zm: the table address is two dependent integer
-        // operations behind zm (multiply-add, mask-and-merge), the grid index itself (:166-167)
-        // is only needed for the check
-        const int kk16 = vg.x + cu_base16;
-        gi = (__float_as_int(zm) - 0x4B400000) + (kk16 >> 4);
-        const unsigned addr = (((unsigned)__float_as_int(zm) * 16u + (unsigned)kk16) & (16 * PLL_CANDS - 16)) | tab_a;
-        // the candidate that IS trigArg(u) carries Kp*errorD, Ki*errorD of sample u+1 and proves it
-        int4 e;
-        asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(addr) : "memory");
-        kpe = __int_as_float(e.x);
-        kie = __int_as_float(e.y);
-        bad |= (e.z ^ gi) | (e.w ^ (u + 1));
+        const int kk = vg.x + kbase;
+        const int t1 = rb.z - kk;
+        const bool h0 = zm == __int_as_float(t1 - 1), h1 = zm == __int_as_float(t1), h2 = zm == __int_as_float(t1 + 1);
+        gi = __float_as_int(zm) + kk;                                 // :166-167 as a grid index (parked; off the chain)
+        bad |= (rb.w ^ stamp) | (int)!(h0 || h1 || h2);
+        if (!last) {
+            const float i0 = p_faddf(integ, kie0), i1 = p_faddf(integ, kie1), i2 = p_faddf(integ, kie2);     // :163
+            const float p0 = p_faddf(ph, p_faddf(kpe0, i0)), p1 = p_faddf(ph, p_faddf(kpe1, i1)), p2 = p_faddf(ph, p_faddf(kpe2, i2));   // :164
+            integ = h0 ? i0 : (h2 ? i2 : i1);
+            ph = h0 ? p0 : (h2 ? p2 : p1);
+        } else {
+            kpe = h0 ? kpe0 : (h2 ? kpe2 : kpe1);
+            kie = h0 ? kie0 : (h2 ? kie2 : kie1);
+        }
         const float frac = p_faddf(z, -p_faddf(zm, -12582912.0f));
         worst = fmaxf(worst, __fmaf_rn(fmaxf(fabsf(tt), 4.0f), 0x1p-22f, fabsf(frac)));
     };
     auto load_vg = [&](unsigned addr) {
         int2 v;
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+        return v;
+    };
+    auto load_half = [&](unsigned addr) {
+        int4 v;
+        asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
         return v;
     };
     // after a block: if a guard failed in it, the same block again, the exact way (rare)
@@ -695,28 +724,40 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
     };
     int t = 0;
     bool fatal = false;
-    int2 vg0 = load_vg(in_base + (unsigned)(base & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
     const int n_full = cnt >> 4;
     for (int b = 0; b < n_full; b++, t += 16) {
         const int u0 = base + t;
-        // the state before the block, in case it has to be stepped the exact way
+        // the state before the block (after sample u0-1, with Kp*errorD, Ki*errorD of sample u0
+        // pending), in case it has to be stepped the exact way
         const float integ0 = integ, ph0 = ph;
         const int gi0 = gi;
+        integ = p_faddf(integ, kie);                                  // :163 of sample u0
+        ph = p_faddf(ph, p_faddf(kpe, integ));                       // :164
         // neither the rings nor the tables wrap inside a block of 16 (all sizes are multiples
         // of 16 and u0 is one): addresses are base + constant
         const unsigned in_a0 = in_base + (unsigned)(u0 & (PLL_RING - 1)) * (unsigned)sizeof(PllIn);
-        const unsigned tab_a0 = tab_base + (unsigned)(u0 & (PLL_TABLES - 1)) * (16u * PLL_CANDS);
-        const int2 vg_next_block = load_vg(in_base + (unsigned)((u0 + 16) & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
+        const unsigned tab_a0 = tab_base + (unsigned)(u0 & (PLL_TABLES - 1)) * (unsigned)sizeof(PllRow);
+        const int stamp = u0 + 1;
         int gis[16];
-        int2 vg = vg0;
+        // tables and {vi, vr} are fetched two steps ahead -- late enough for the candidate warps,
+        // early enough to be off the chain; the key half of a table before its other half
+        int4 rb0 = load_half(tab_a0 + 16u), ra0 = load_half(tab_a0);
+        int4 rb1 = load_half(tab_a0 + (unsigned)sizeof(PllRow) + 16u), ra1 = load_half(tab_a0 + (unsigned)sizeof(PllRow));
+        int2 vg0 = load_vg(in_a0), vg1 = load_vg(in_a0 + (unsigned)sizeof(PllIn));
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-            const int2 vg_n = (j < 15) ? load_vg(in_a0 + (unsigned)(j + 1) * (unsigned)sizeof(PllIn)) : vg_next_block;
-            step(u0 + j, tab_a0 + (unsigned)j * (16u * PLL_CANDS), vg);
+            int4 rb2 = rb1, ra2 = ra1;
+            int2 vg2 = vg1;
+            if (j + 2 < 16) {
+                rb2 = load_half(tab_a0 + (unsigned)(j + 2) * (unsigned)sizeof(PllRow) + 16u);
+                ra2 = load_half(tab_a0 + (unsigned)(j + 2) * (unsigned)sizeof(PllRow));
+                vg2 = load_vg(in_a0 + (unsigned)(j + 2) * (unsigned)sizeof(PllIn));
+            }
+            step(ra0, rb0, vg0, stamp, j == 15);
             gis[j] = gi;
-            vg = vg_n;
+            ra0 = ra1; rb0 = rb1; vg0 = vg1;
+            ra1 = ra2; rb1 = rb2; vg1 = vg2;
         }
-        vg0 = vg_next_block;
         // park the 16 grid indices for the I/O warp (every lane the same stores)
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
@@ -734,10 +775,14 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
         const int u0 = base + t, nb = cnt - t;
         const float integ0 = integ, ph0 = ph;
         const int gi0 = gi;
+        integ = p_faddf(integ, kie);
+        ph = p_faddf(ph, p_faddf(kpe, integ));
         for (int j = 0; j < nb; j++) {
             const int u = u0 + j;
+            const unsigned row = tab_base + (unsigned)(u & (PLL_TABLES - 1)) * (unsigned)sizeof(PllRow);
+            const int4 rb = load_half(row + 16u), ra = load_half(row);
             const int2 vg = load_vg(in_base + (unsigned)(u & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
-            step(u, tab_base + (unsigned)(u & (PLL_TABLES - 1)) * (16u * PLL_CANDS), vg);
+            step(ra, rb, vg, u0 + 1, j == nb - 1);
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(gi) : "memory");
         }
         fatal = !settle(u0, nb, integ0, ph0, gi0);
@@ -759,9 +804,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     __shared__ __align__(16) int2 s_ph[PLL_PH_RING];  // {predicted phaseEst, step + 1}, written by the predictor warp
     __shared__ float s_hdr[2];                        // integrator, phaseEst at the start of the group (warp 0 -> predictor)
     __shared__ int s_prog;                            // steps of the capture warp 0 has completed (per block of 16), or PLL_ABANDONED
-    // candidate tables, indexed by (step & 63, grid index & 15): {Kp*errorD, Ki*errorD of the next
-    // sample, grid index, step+1 (negated if a guard failed)}; one self-validating 16-byte record per lane
-    __shared__ __align__(16 * PLL_CANDS) int4 s_tab[PLL_TABLES][PLL_CANDS];   // row-aligned: warp 0 ORs the entry offset into the row address
+    __shared__ PllRow s_tab[PLL_TABLES];              // candidate tables, a ring over the steps
     __shared__ __align__(16) int s_g[2][PLL_GROUP];                 // grid index of each trigArg of the group, double-buffered
     __shared__ double s_grid[2];                      // ulp, 1/ulp of the current group
     __shared__ double s_prep_ulp[4];                  // ulp the ring slots of each group were prepared with
@@ -805,7 +848,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             in.v = __dmul_rn(k.w, (double)toff);
             // v on the float grid of the current binade: integer part and remainder
             const double qv = grid_round(in.v, s_grid[1]);
-            in.vi16 = grid_index(qv) << 4;
+            in.vi = grid_index(qv);
             in.vr = __double2float_rn(__fma_rn(in.v, s_grid[1], -p_add(qv, -FMRX_RINT_MAGIC)));
             in.c = predictor_c(k, pvv, (float)min(t0 + u, 16777216));      // trigOffset BEFORE this step
             in.pad = 0;
@@ -817,8 +860,10 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
 
     if (threadIdx.x < PLL_PH_RING)
         s_ph[threadIdx.x] = make_int2(0, 0);
-    for (int i = threadIdx.x; i < PLL_TABLES * PLL_CANDS; i += PLL_THREADS)
-        s_tab[i / PLL_CANDS][i % PLL_CANDS] = make_int4(0, 0, 0, (int)0x80000000);
+    for (int i = threadIdx.x; i < PLL_TABLES; i += PLL_THREADS) {
+        s_tab[i].keyC = PLL_ROW_INVALID;
+        s_tab[i].stamp = 0;
+    }
     if (threadIdx.x == 0)
         s_flag[1] = 0;
     // warp 0 owns the recurrence state
@@ -905,12 +950,11 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 const long long dbg_w0 = clock64();
                 dbg_pre += dbg_w0 - dbg_ga;
                 {   // lane t watches table t
-                    const int want = base + lane + 1;
                     const bool need = lane < 16 && lane < cnt;           // the first block's tables
                     int spin = 0;
                     for (;;) {
-                        const int z = ld_v4(&s_tab[(base + lane) & (PLL_TABLES - 1)][0]).w;
-                        if (__all_sync(0xffffffffu, !need || z == want || z == -want) || ++spin >= PLL_SPIN_LIMIT)
+                        const int z = ld_v4(&s_tab[(base + (lane & 15)) & (PLL_TABLES - 1)].kpe2).w;      // the stamp
+                        if (__all_sync(0xffffffffu, !need || z == base + 1) || ++spin >= PLL_SPIN_LIMIT)
                             break;
                     }
                     if (spin >= PLL_SPIN_LIMIT) {
@@ -931,11 +975,11 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 r.kie = kie;
                 r.inv_ulp_f = inv_ulp_f;
                 r.pi_f = pi_f;
-                r.cu_base16 = (cu_base + 0x4B400000) << 4;                      // 16 * rint(phaseEst/ulp), |.| < 2^25
+                r.kbase = cu_base;
                 r.base = base;
                 r.cnt = cnt;
                 r.in_base = smem_u32(&s_in[0]) + 32u;                            // offset of {vi, vr} in a slot
-                r.tab_base = smem_u32(&s_tab[0][0]);
+                r.tab_base = smem_u32(&s_tab[0]);
                 r.sg_base = smem_u32(&s_g[g & 1][0]);
                 r.prog_addr = smem_u32(&s_prog);
                 r.gi = __double2int_rn(p_mul(ch.tad, inv_ulp));                  // exact: trigArg is on the grid
@@ -992,30 +1036,27 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             }
         } else if (role >= 2) {
             // ================= candidate tables =================
-            // A warp evaluates two consecutive steps at once, one per half-warp (16 grid points
-            // each): steps base + 2*cand_id + {0, 1} (mod 2*PLL_CAND_WARPS), each centred on the
-            // predictor's phaseEst for that very step.
+            // A warp evaluates eight consecutive steps at once, one per quad of lanes: lane 4*s + j
+            // takes step base + 8*cand_id + s (mod 8*PLL_CAND_WARPS) and the grid point G_c - 1 + j
+            // around the predictor's trigArg of that step (j = 3 is idle work: SIMT).
             if (spec) {
-                const int half = lane >> 4, hl = lane & (PLL_CANDS - 1);
+                const int sq = lane >> 2, jq = lane & 3;
                 const unsigned prog_a = smem_u32(&s_prog);
                 auto progress = [&]() {
                     int v;
                     asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(prog_a) : "memory");
                     return v;
                 };
-                for (int t2 = 2 * cand_id; t2 < cnt; t2 += 2 * PLL_CAND_WARPS) {
-                    const bool live = t2 + half < cnt;
-                    const int ue = base + t2;                            // the even step of the pair
-                    const int u = ue + (live ? half : 0);
+                for (int t8 = PLL_BATCH * cand_id; t8 < cnt; t8 += PLL_BATCH * PLL_CAND_WARPS) {
+                    const bool live = t8 + sq < cnt;
+                    const int u = base + t8 + (live ? sq : 0);
                     const double v = s_in[u & (PLL_RING - 1)].v;
                     const PllIn nx = s_in[(u + 1) & (PLL_RING - 1)];     // the sample the result is for
-                    // the predictor publishes in order: once the later record of the pair is there, both are
-                    const int last = min(ue + 1, base + cnt - 1);
-                    int4 pr;
+                    // the predictor publishes in order: once the last record of the batch is there, all are
+                    const int last = min(base + t8 + PLL_BATCH - 1, base + cnt - 1);
                     int prog = 0, spin = 0;
                     for (;; spin++) {
-                        pr = ld_v4(&s_ph[ue & (PLL_PH_RING - 1)]);       // {phaseEst(ue), ue + 1, phaseEst(ue + 1), ue + 2}
-                        const int seq = (last == ue) ? pr.y : pr.w;
+                        const int seq = ld_v2(&s_ph[last & (PLL_PH_RING - 1)]).y;
                         if (seq - (last + 1) >= 0 || spin >= PLL_SPIN_LIMIT)
                             break;
                         if ((spin & 7) == 7 && (prog = progress()) == PLL_ABANDONED)
@@ -1023,25 +1064,28 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     }
                     if (prog == PLL_ABANDONED)
                         break;
-                    if (pr.y != ue + 1) {            // timed out, or this warp fell a whole ring behind: no table
-                        if (spin >= PLL_SPIN_LIMIT) {
-                            s_flag[1] = 1;
-                            break;
-                        }
-                        continue;
+                    if (spin >= PLL_SPIN_LIMIT) {
+                        s_flag[1] = 1;
+                        break;
                     }
-                    // this lane's grid point: the one congruent to `hl` (mod 16) in [G_c-8, G_c+7]
-                    const float php = __int_as_float(half ? pr.z : pr.x);
-                    const int gc = grid_index(grid_round(p_add(v, (double)php), inv_ulp));
-                    const int gl = gc - PLL_CANDS / 2 + ((hl - (gc - PLL_CANDS / 2)) & (PLL_CANDS - 1));
+                    const int2 pr = ld_v2(&s_ph[u & (PLL_PH_RING - 1)]);
+                    // (a record that is not this step's: the warp fell a whole ring behind -- no table then)
+                    const bool have = pr.y == u + 1;
+                    // this lane's grid point: G_c - 1 + j
+                    const int gc = grid_index(grid_round(p_add(v, (double)__int_as_float(pr.x)), inv_ulp));
+                    const int gl = gc - 1 + jq;
                     const double tad = p_mul((double)gl, ulp);                        // exact
                     const Feedback f = make_feedback(K, tad, i2d(nx.turn_hi, 0), nx.inv_x, nullptr, nullptr);
                     // the float grid of the binade is only right strictly inside it
                     const int ag = gl < 0 ? -gl : gl;
-                    bool ok = ag > (1 << 23) && ag < (1 << 24);
+                    bool ok = have && ag > (1 << 23) && ag < (1 << 24);
                     const float ed = error_from_feedback(f, nx.x, nx.xd, ok);         // :159-161 of sample u+1
-                    // the rows still hold the tables of steps ue - 64, ue - 63: wait until warp 0 is past them
-                    for (spin = 0; (prog = progress()) != PLL_ABANDONED && prog - (ue + 2 - PLL_TABLES) < 0 && spin < PLL_SPIN_LIMIT; spin++)
+                    // the table is good if the guards of its three grid points held
+                    const unsigned oks = __ballot_sync(0xffffffffu, ok || jq == 3);
+                    const bool valid = ((oks >> (4 * sq)) & 7u) == 7u;
+                    // the rows still hold the tables of steps u - PLL_TABLES: wait until warp 0 is past them
+                    for (spin = 0; (prog = progress()) != PLL_ABANDONED && prog - (base + t8 + PLL_BATCH - PLL_TABLES) < 0 && spin < PLL_SPIN_LIMIT;
+                         spin++)
                         ;
                     if (prog == PLL_ABANDONED)
                         break;
@@ -1049,9 +1093,14 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                         s_flag[1] = 1;
                         break;
                     }
-                    if (live)
-                        st_v4(&s_tab[u & (PLL_TABLES - 1)][hl], __float_as_int(p_fmulf(k.kp, ed)), __float_as_int(p_fmulf(k.ki, ed)), gl,
-                              ok ? u + 1 : -(u + 1));
+                    // one store instruction writes the eight tables: 8 bytes per lane, 32 per quad
+                    if (live) {
+                        const int lo = jq < 3 ? __float_as_int(p_fmulf(k.kp, ed)) : (valid ? gc : PLL_ROW_INVALID);
+                        const int hi = jq < 3 ? __float_as_int(p_fmulf(k.ki, ed)) : (u & ~15) + 1;
+                        asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(smem_u32(&s_tab[u & (PLL_TABLES - 1)]) + 8u * (unsigned)jq),
+                                     "r"(lo), "r"(hi)
+                                     : "memory");
+                    }
                 }
             }
         } else if (warp == PLL_PRED_WARP) {

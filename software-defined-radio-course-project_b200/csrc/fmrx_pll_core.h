@@ -454,8 +454,7 @@ FMRX_HD float chain_step(Chain &c, const Consts &k, const TrigK &K, float x, uns
 // wrap(pi*(x < 0) - t) onto (-pi, pi].  With t = w*trigOffset + phaseEst, the part that
 // does not depend on the recurrence,
 //     c = pi*(x < 0) - (w*trigOffset mod 2 pi),
-// is prepared per sample, and one predictor step is five float operations for the phase
-// detector plus the reference's own four for the loop filter.  The predictor is never
+// is prepared per sample, and one predictor step is a handful of float operations.  The predictor is never
 // used for a result: it only says where to CENTRE the candidate table of a step, and it
 // restarts from the exact (integrator, phaseEst) at every group.  While the loop is
 // locked its phaseEst stays within a grid step of the exact one over a group
@@ -468,13 +467,20 @@ FMRX_HD float predictor_c(const Consts &k, float x, float toff_before)
     return p_d2f(p_add(x < 0.0f ? 3.141592653589793 : 0.0, -rp));
 }
 
+// integ' = integ + Ki e and ph' = ph + Kp e + integ' = (ph + integ) + (Kp + Ki) e, with
+// e = d - 2 pi k, d = c - ph, k = rint(d / 2 pi): arranged so that only five float
+// operations depend on each other from one phaseEst to the next (d, d/2pi, two for the
+// rint, one FMA); the roundings differ from the reference's, which is all the same to a
+// predictor.
 FMRX_HD void predictor_step(const Consts &k, float c, float &integ, float &ph)
 {
+    const float kpi = p_faddf(k.kp, k.ki);
     const float d = p_faddf(c, -ph);
+    const float phi = p_faddf(ph, integ);
+    const float a = p_fmaf(kpi, d, phi);                             // beside the rint
     const float kq = p_faddf(p_faddf(p_fmulf(d, 0.15915494f), 12582912.0f), -12582912.0f);   // rint(d / 2 pi)
-    const float e = p_fmaf(-kq, 6.2831855f, d);
-    integ = p_faddf(integ, p_fmulf(k.ki, e));                        // :163
-    ph = p_faddf(ph, p_faddf(p_fmulf(k.kp, e), integ));              // :164
+    ph = p_fmaf(-kq, p_fmulf(kpi, 6.2831855f), a);                   // :164
+    integ = p_fmaf(k.ki, p_fmaf(-kq, 6.2831855f, d), integ);         // :163
 }
 
 // trigOffset advances by float additions of 1 (:166).  From an integer-valued start

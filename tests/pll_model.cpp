@@ -82,7 +82,7 @@ void pll_model_sincos_d(const float *x, int n, double *s, double *c)
 // and record, per group, the largest distance (in float grid steps of trigArg) between the
 // exact trigArg and the grid point the predictor would centre the candidate table on.
 // state5 as in pll_model_run; worst[n_groups].
-int pll_model_predict(const float *pilot, int n, float freq, float Fs, float bw, float *state5, int group, int *worst)
+int pll_model_predict(const float *pilot, int n, float freq, float Fs, float bw, float *state5, int group, int *worst, long long *hist)
 {
     Consts k;
     k.kp = bw * 2.666f;
@@ -108,6 +108,11 @@ int pll_model_predict(const float *pilot, int n, float freq, float Fs, float bw,
             const double d = fabs((double)ta / ulp - nearbyint((v + (double)pp) / ulp));
             if (ta != 0.0f && d > w)
                 w = d > 1e9 ? 1000000000 : (int)d;
+            if (hist && ng >= 1 && ta != 0.0f) {
+                const double sd = (double)ta / ulp - nearbyint((v + (double)pp) / ulp);
+                int b = (int)sd + 8;
+                hist[b < 0 ? 0 : b > 16 ? 16 : b]++;
+            }
         }
         worst[ng] = w;
     }

@@ -116,8 +116,11 @@ def test_predictor_tracks_the_exact_recurrence(model, port, synth, mode, seed, p
     worst = np.zeros((len(pilot) + group - 1) // group, np.int32)
     state = np.array([0.0, 0.0, 1.0, 0.0, 0.0], np.float32)
     model.pll_model_predict.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, f32p, C.c_int,
-                                        C.POINTER(C.c_int)]
+                                        C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
+    hist = np.zeros(17, np.int64)           # signed distance + 8, groups after the first
     ng = model.pll_model_predict(pilot.ctypes.data_as(f32p), len(pilot), 19000.0, float(info.if_fs), 0.01,
-                                 state.ctypes.data_as(f32p), group, worst.ctypes.data_as(C.POINTER(C.c_int)))
+                                 state.ctypes.data_as(f32p), group, worst.ctypes.data_as(C.POINTER(C.c_int)),
+                                 hist.ctypes.data_as(C.POINTER(C.c_longlong)))
+    print("distance histogram (-8..+8):", hist.tolist())
     assert ng == len(worst)
     assert worst[1:].max() <= 2, worst[:20]

@@ -9,5 +9,5 @@ for l in sys.stdin:
               "first_call_ns", round(d.get("first_call_pll_ns_per_sample", 0), 1), "diag", d["pll_groups_last_chunk"],
               d["pll_groups_redone_last_chunk"], "rf", round(d["rf_demod_ms"], 2), "bp", round(d["bandpass_ms"], 2), "au",
               round(d["audio_ms"], 2))
-    elif l.startswith("pll dbg:"):
+    elif l.startswith("pll dbg"):
         print(l[:330])
