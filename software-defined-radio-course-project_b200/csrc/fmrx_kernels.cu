@@ -459,7 +459,7 @@ constexpr int PLL_WARPS = 12;
 constexpr int PLL_THREADS = 32 * PLL_WARPS;
 constexpr int PLL_CAND_WARPS = 6;        // warps 2,3,6,7,10,11 (schedulers 2 and 3), eight steps each: one per quad of lanes
 constexpr int PLL_BATCH = 8;             // steps per pass of a candidate warp
-constexpr int PLL_ROW_INVALID = 0x40000000;   // centre key of a table none of warp 0's grid points can match (|grid index| < 2^24)
+constexpr float PLL_ROW_INVALID = 0x1p100f;   // lq of a table nothing matches
 constexpr int PLL_IO_WARPS = 2;          // warps 1, 5 (scheduler 1); warps 4 and 8 (warp 0's scheduler) only take part in the barriers
 constexpr int PLL_PRED_WARP = 9;         // the run-ahead predictor (scheduler 1)
 constexpr int PLL_GROUP = 1024;          // steps between checkpoints / barriers
@@ -575,7 +575,8 @@ __device__ __noinline__ bool pll_block_exact(TableRun &r, int u0, int nsteps, co
         if (!chain_step_fast(c, r.k, K, in))
             chain_step_generic(c, r.k, i.x);
         const int g = grid_index(grid_round(c.tad, c.inv_ulp));
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(r.sg_base + 4u * (unsigned)(u - r.base)), "r"(g));
+        // parked like the table steps do: the grid index less (vi + kbase)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(r.sg_base + 4u * (unsigned)(u - r.base)), "r"(g - i.vi - r.kbase));
         gi = g;
     }
     if (c.binade == FMRX_DISARMED || c.ulp != r.ulp)
@@ -645,9 +646,10 @@ __device__ __noinline__ void pll_group_checked(pllcore::Chain &chain, const pllc
 // 16-byte halves -- the half with the key and the block stamp FIRST, so that a half
 // overwritten in between can only fail the check, never pass it.
 struct __align__(32) PllRow {
-    float kpe0, kie0, kpe1, kie1;    // Kp*errorD, Ki*errorD of the next sample if trigArg is grid point keyC - 1, keyC
-    float kpe2, kie2;                // ... keyC + 1
-    int keyC;                        // the centre grid point (PLL_ROW_INVALID: a candidate's guard failed)
+    float kpe0, kie0, kpe1, kie1;    // Kp*errorD, Ki*errorD of the next sample if trigArg is grid point G_c - 1, G_c
+    float kpe2, kie2;                // ... G_c + 1
+    float lq;                        // n1 - 1/2, n1 = G_c - (vi + kbase) - bits(1.5 * 2^23): trigArg IS G_c iff rint(z) = n1,
+                                     // z = phaseEst/ulp - pi + vr as warp 0 computes it (PLL_ROW_INVALID if a guard failed)
     int stamp;                       // (step & ~15) + 1: which block of 16 steps of the launch the table is for
 };
 
@@ -659,39 +661,63 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
     const int kbase = r.kbase, base = r.base, cnt = r.cnt;
     const unsigned in_base = r.in_base, tab_base = r.tab_base, sg_base = r.sg_base, prog_addr = r.prog_addr;
     int bad = 0, gi = r.gi, n_exact = 0;
-    float worst = 0.0f;
+    float ttmax = 0.0f, fracmax = 0.0f, dmax = 0.0f;
+    // (a, b) = t < lo ? (a0, b0) : t > hi ? (a2, b2) : (a1, b1), as selects on the data path (a predicated
+    // instruction waits longer for its predicate than a select does)
+    auto pick = [](float t, float lo, float hi, float a0, float a1, float a2, float b0, float b1, float b2, float &a, float &b) {
+        asm("{ .reg .pred q0, q2;\n\t"
+            "setp.lt.f32 q0, %2, %3;\n\t"
+            "setp.gt.f32 q2, %2, %4;\n\t"
+            "selp.f32 %0, %5, %6, q0;\n\t"
+            "selp.f32 %1, %8, %9, q0;\n\t"
+            "selp.f32 %0, %7, %0, q2;\n\t"
+            "selp.f32 %1, %10, %1, q2; }"
+            : "=&f"(a), "=&f"(b)
+            : "f"(t), "f"(lo), "f"(hi), "f"(a0), "f"(a1), "f"(a2), "f"(b0), "f"(b1), "f"(b2));
+    };
     // One step: from (integrator, phaseEst) after sample u, the table of step u and {vi, vr} of
     // sample u to the state after sample u+1 -- or, with `last`, to Kp*errorD, Ki*errorD of sample
     // u+1 (what a block hands to the next one and to the exact fall-back).
-    //   - three hypotheses: trigArg(u) is grid point keyC-1, keyC, keyC+1; for each the loop filter
-    //     (:163-164) of sample u+1 -- nine float additions that only need the state, not the index;
-    //   - the index (:166-167): zm = (fma(phaseEst, 1/ulp, -pi) + vr) + 1.5*2^23 holds the grid index
-    //     less (vi + pi) in its low bits, so hypothesis j is right iff zm == the float whose bits are
-    //     keyC + j - 1 - (vi + kbase): three float compares against values ready long before;
-    //   - two predicated moves pick the state.  On the dependent chain: FFMA, FADD, FADD, compare,
-    //     move -- the three additions of the loop filter run beside it.
-    auto step = [&](int4 ra, int4 rb, int2 vg, int stamp, bool last) {
+    //   - three hypotheses: trigArg(u) is grid point G_c-1, G_c, G_c+1; for each the loop filter
+    //     (:163-164) of sample u+1 -- float additions that need the state but not the index;
+    //   - which one: trigArg(u) is the float nearest w*trigOffset + phaseEst (:166-167), i.e. grid
+    //     point vi + pi + rint(z), z = t + vr, t = fma(phaseEst, 1/ulp, -pi).  So G_c - 1 iff
+    //     z < n1 - 1/2 iff t < (n1 - 1/2) - vr, and G_c + 1 iff t > (n1 + 1/2) - vr: two compares of t
+    //     against values ready long before; two selects pick the state.
+    // On the dependent chain: one FFMA, a compare, two selects.  Everything else -- z, its
+    // rint (parked: the grid index less vi + kbase), the guards -- hangs off t beside the chain.
+    // Guards (they only accumulate; the block is stepped again the exact way if one fails):
+    //   - the table is this block's (stamp);
+    //   - |z - n1| < 3/2: the grid point is one of the three;
+    //   - z is clear of a tie by 2^-21 * max(|t|, 4).  Error budget, in grid steps: t <= 2^-24 |t|,
+    //     vr 2^-25, the two thresholds <= 2^-24 (|n1| + 2) each, z (for this guard) <= 2^-24 (|t| + 1),
+    //     the reference's own double rounding of the sum < 2^-29; with |n1| <= |t| + 2 that is below
+    //     2^-24 (5 |t| + 9), and 2^-21 * max(|t|, 4) = 2^-24 * 8 max(|t|, 4) is above it.
+    auto step = [&](int4 ra, int4 rb, int2 vg, int stamp, bool last) -> int {
         const float kpe0 = __int_as_float(ra.x), kie0 = __int_as_float(ra.y), kpe1 = __int_as_float(ra.z), kie1 = __int_as_float(ra.w);
         const float kpe2 = __int_as_float(rb.x), kie2 = __int_as_float(rb.y);
+        const float lq = __int_as_float(rb.z), vr = __int_as_float(vg.y);
+        const float lp = p_faddf(lq, -vr), hp = p_faddf(lp, 1.0f);
         const float tt = __fmaf_rn(ph, inv_ulp_f, -pi_f);
-        const float z = p_faddf(tt, __int_as_float(vg.y));
-        const float zm = p_faddf(z, 12582912.0f);                     // 1.5 * 2^23: rint in the low bits
-        const int kk = vg.x + kbase;
-        const int t1 = rb.z - kk;
-        const bool h0 = zm == __int_as_float(t1 - 1), h1 = zm == __int_as_float(t1), h2 = zm == __int_as_float(t1 + 1);
-        gi = __float_as_int(zm) + kk;                                 // :166-167 as a grid index (parked; off the chain)
-        bad |= (rb.w ^ stamp) | (int)!(h0 || h1 || h2);
         if (!last) {
             const float i0 = p_faddf(integ, kie0), i1 = p_faddf(integ, kie1), i2 = p_faddf(integ, kie2);     // :163
             const float p0 = p_faddf(ph, p_faddf(kpe0, i0)), p1 = p_faddf(ph, p_faddf(kpe1, i1)), p2 = p_faddf(ph, p_faddf(kpe2, i2));   // :164
-            integ = h0 ? i0 : (h2 ? i2 : i1);
-            ph = h0 ? p0 : (h2 ? p2 : p1);
+            pick(tt, lp, hp, i0, i1, i2, p0, p1, p2, integ, ph);
         } else {
-            kpe = h0 ? kpe0 : (h2 ? kpe2 : kpe1);
-            kie = h0 ? kie0 : (h2 ? kie2 : kie1);
+            pick(tt, lp, hp, kpe0, kpe1, kpe2, kie0, kie1, kie2, kpe, kie);
         }
-        const float frac = p_faddf(z, -p_faddf(zm, -12582912.0f));
-        worst = fmaxf(worst, __fmaf_rn(fmaxf(fabsf(tt), 4.0f), 0x1p-22f, fabsf(frac)));
+        const float z = p_faddf(tt, vr);
+        const float zm = p_faddf(z, 12582912.0f);                     // 1.5 * 2^23: rint in the low bits
+        bad |= rb.w ^ stamp;
+        dmax = fmaxf(dmax, fabsf(p_faddf(z, -p_faddf(lq, 0.5f))));
+        ttmax = fmaxf(ttmax, fabsf(tt));
+        fracmax = fmaxf(fracmax, fabsf(p_faddf(z, -p_faddf(zm, -12582912.0f))));
+        return __float_as_int(zm);
+    };
+    // the guards of a block: the tie margin (the block's largest |t| for all of its steps), one of
+    // the three hypotheses at every step, every table this block's
+    auto guards_failed = [&]() {
+        return bad != 0 || !(dmax < 1.5f) || !(__fmaf_rn(fmaxf(ttmax, 4.0f), 0x1p-21f, fracmax) < 0.5f);
     };
     auto load_vg = [&](unsigned addr) {
         int2 v;
@@ -705,7 +731,7 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
     };
     // after a block: if a guard failed in it, the same block again, the exact way (rare)
     auto settle = [&](int u0, int nb, float integ0, float ph0, int gi0) -> bool {
-        if (bad != 0 || !(worst < 0.5f)) {
+        if (guards_failed()) {
             r.integ = integ0;            // by value through r: nothing on the chain has its address taken
             r.ph = ph0;
             r.gi = gi0;
@@ -717,9 +743,9 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
             kpe = r.kpe;
             kie = r.kie;
             gi = r.gi;
-            bad = 0;
-            worst = 0.0f;
         }
+        bad = 0;
+        ttmax = fracmax = dmax = 0.0f;
         return true;
     };
     int t = 0;
@@ -753,12 +779,13 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
                 ra2 = load_half(tab_a0 + (unsigned)(j + 2) * (unsigned)sizeof(PllRow));
                 vg2 = load_vg(in_a0 + (unsigned)(j + 2) * (unsigned)sizeof(PllIn));
             }
-            step(ra0, rb0, vg0, stamp, j == 15);
-            gis[j] = gi;
+            gis[j] = step(ra0, rb0, vg0, stamp, j == 15);
+            if (j == 15)
+                gi = gis[15] + vg0.x + kbase;                         // the block's last grid index (:166-167)
             ra0 = ra1; rb0 = rb1; vg0 = vg1;
             ra1 = ra2; rb1 = rb2; vg1 = vg2;
         }
-        // park the 16 grid indices for the I/O warp (every lane the same stores)
+        // park the bits of the 16 zm's for the I/O warp (every lane the same stores)
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(gis[j]), "r"(gis[j + 1]),
@@ -782,8 +809,9 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
             const unsigned row = tab_base + (unsigned)(u & (PLL_TABLES - 1)) * (unsigned)sizeof(PllRow);
             const int4 rb = load_half(row + 16u), ra = load_half(row);
             const int2 vg = load_vg(in_base + (unsigned)(u & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
-            step(ra, rb, vg, u0 + 1, j == nb - 1);
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(gi) : "memory");
+            const int zb = step(ra, rb, vg, u0 + 1, j == nb - 1);
+            gi = zb + vg.x + kbase;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(zb) : "memory");
         }
         fatal = !settle(u0, nb, integ0, ph0, gi0);
     }
@@ -803,6 +831,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     PllIn *s_in = reinterpret_cast<PllIn *>(pll_dyn_smem);      // [PLL_RING]
     __shared__ __align__(16) int2 s_ph[PLL_PH_RING];  // {predicted phaseEst, step + 1}, written by the predictor warp
     __shared__ float s_hdr[2];                        // integrator, phaseEst at the start of the group (warp 0 -> predictor)
+    __shared__ int s_kbase;                           // rint(phaseEst/ulp) at the start of the group, less the bits of 1.5 * 2^23
+    __shared__ int s_kb_hist[2];                      // ... of the group whose parked values are in s_g[.]
     __shared__ int s_prog;                            // steps of the capture warp 0 has completed (per block of 16), or PLL_ABANDONED
     __shared__ PllRow s_tab[PLL_TABLES];              // candidate tables, a ring over the steps
     __shared__ __align__(16) int s_g[2][PLL_GROUP];                 // grid index of each trigArg of the group, double-buffered
@@ -861,7 +891,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     if (threadIdx.x < PLL_PH_RING)
         s_ph[threadIdx.x] = make_int2(0, 0);
     for (int i = threadIdx.x; i < PLL_TABLES; i += PLL_THREADS) {
-        s_tab[i].keyC = PLL_ROW_INVALID;
+        s_tab[i].lq = PLL_ROW_INVALID;
         s_tab[i].stamp = 0;
     }
     if (threadIdx.x == 0)
@@ -910,6 +940,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 s_grid[0] = ch.ulp;
                 s_grid[1] = ch.inv_ulp;
                 s_flag[2] = s_prep_ulp[(g + 1) & 3] != ch.ulp;
+                s_kbase = __float_as_int(p_faddf(p_fmulf(ch.ph, (float)ch.inv_ulp), 12582912.0f)) - 0x4B400000 - 0x4B400000;
                 s_hdr[0] = ch.integ;
                 s_hdr[1] = ch.ph;
                 s_prog = base;
@@ -1033,6 +1064,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             if (lane == 0) {
                 s_spec[g & 1] = good ? 1 : 0;
                 s_ulp_hist[g & 1] = ulp;
+                s_kb_hist[g & 1] = s_kbase;
             }
         } else if (role >= 2) {
             // ================= candidate tables =================
@@ -1051,6 +1083,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const bool live = t8 + sq < cnt;
                     const int u = base + t8 + (live ? sq : 0);
                     const double v = s_in[u & (PLL_RING - 1)].v;
+                    const int vi = s_in[u & (PLL_RING - 1)].vi;
                     const PllIn nx = s_in[(u + 1) & (PLL_RING - 1)];     // the sample the result is for
                     // the predictor publishes in order: once the last record of the batch is there, all are
                     const int last = min(base + t8 + PLL_BATCH - 1, base + cnt - 1);
@@ -1095,7 +1128,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     }
                     // one store instruction writes the eight tables: 8 bytes per lane, 32 per quad
                     if (live) {
-                        const int lo = jq < 3 ? __float_as_int(p_fmulf(k.kp, ed)) : (valid ? gc : PLL_ROW_INVALID);
+                        const int lo = jq < 3 ? __float_as_int(p_fmulf(k.kp, ed))
+                                              : __float_as_int(valid ? p_faddf((float)(gc - (vi + s_kbase) - 0x4B400000), -0.5f) : PLL_ROW_INVALID);
                         const int hi = jq < 3 ? __float_as_int(p_fmulf(k.ki, ed)) : (u & ~15) + 1;
                         asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(smem_u32(&s_tab[u & (PLL_TABLES - 1)]) + 8u * (unsigned)jq),
                                      "r"(lo), "r"(hi)
@@ -1150,8 +1184,10 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             if (g > 0) {                     // previous group: always complete
                 const int pb = base - PLL_GROUP;
                 for (int j = lane + 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS)
-                    tr[pb + j] = s_spec[(g - 1) & 1] ? __double2float_rn(p_mul((double)s_g[(g - 1) & 1][j], s_ulp_hist[(g - 1) & 1]))
-                                                     : __int_as_float(s_g[(g - 1) & 1][j]);
+                    tr[pb + j] = s_spec[(g - 1) & 1]
+                                     ? __double2float_rn(p_mul((double)(s_g[(g - 1) & 1][j] + s_in[(pb + j) & (PLL_RING - 1)].vi + s_kb_hist[(g - 1) & 1]),
+                                                               s_ulp_hist[(g - 1) & 1]))
+                                     : __int_as_float(s_g[(g - 1) & 1][j]);
             }
         }
         __syncthreads();
@@ -1160,7 +1196,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     if (warp == 1 && n > 0) {
         const int g = (n - 1) / PLL_GROUP, pb = g * PLL_GROUP;
         for (int j = lane; pb + j < n && j < PLL_GROUP; j += 32)
-            tr[pb + j] = s_spec[g & 1] ? __double2float_rn(p_mul((double)s_g[g & 1][j], s_ulp_hist[g & 1]))
+            tr[pb + j] = s_spec[g & 1] ? __double2float_rn(p_mul((double)(s_g[g & 1][j] + s_in[(pb + j) & (PLL_RING - 1)].vi + s_kb_hist[g & 1]),
+                                                                 s_ulp_hist[g & 1]))
                                        : __int_as_float(s_g[g & 1][j]);
     }
     if ((a.variant & 256) && c == 0 && (warp == 2 || warp == 11) && lane == 0)
