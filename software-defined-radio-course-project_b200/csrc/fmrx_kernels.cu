@@ -525,6 +525,13 @@ __device__ __forceinline__ double i2d(int hi, int lo) { return __hiloint2double(
 // farther than 2^-22 * max(|t|, 4) from a tie therefore rounds the way the reference's sum
 // does; closer ones (about two per million steps) fail the guard and the group is redone
 // the exact way.
+// The grid index of a trigArg from what warp 0 parks for it -- the bits of
+// t = fma(phaseEst, 1/ulp, -pi): vi + pi + rint(t + vr) (:166-167), kbase = pi - bits(1.5 * 2^23).
+__device__ __forceinline__ int parked_index(int t_bits, const PllIn &in, int kbase)
+{
+    return in.vi + kbase + __float_as_int(__fadd_rn(__fadd_rn(__int_as_float(t_bits), in.vr), 12582912.0f));
+}
+
 struct TableRun {
     float integ, ph, kpe, kie;       // in/out: loop filter state; Kp*errorD, Ki*errorD of the sample about to run
     float inv_ulp_f, pi_f;           // 1/ulp (a power of two); rint(phaseEst/ulp) at the group start
@@ -575,8 +582,9 @@ __device__ __noinline__ bool pll_block_exact(TableRun &r, int u0, int nsteps, co
         if (!chain_step_fast(c, r.k, K, in))
             chain_step_generic(c, r.k, i.x);
         const int g = grid_index(grid_round(c.tad, c.inv_ulp));
-        // parked like the table steps do: the grid index less (vi + kbase)
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(r.sg_base + 4u * (unsigned)(u - r.base)), "r"(g - i.vi - r.kbase));
+        // parked like the table steps do: a float t with vi + pi + rint(t + vr) = the grid index
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(r.sg_base + 4u * (unsigned)(u - r.base)),
+                     "r"(__float_as_int(p_faddf((float)(g - i.vi - r.kbase - 0x4B400000), -i.vr))));
         gi = g;
     }
     if (c.binade == FMRX_DISARMED || c.ulp != r.ulp)
@@ -648,8 +656,8 @@ __device__ __noinline__ void pll_group_checked(pllcore::Chain &chain, const pllc
 struct __align__(32) PllRow {
     float kpe0, kie0, kpe1, kie1;    // Kp*errorD, Ki*errorD of the next sample if trigArg is grid point G_c - 1, G_c
     float kpe2, kie2;                // ... G_c + 1
-    float lq;                        // n1 - 1/2, n1 = G_c - (vi + kbase) - bits(1.5 * 2^23): trigArg IS G_c iff rint(z) = n1,
-                                     // z = phaseEst/ulp - pi + vr as warp 0 computes it (PLL_ROW_INVALID if a guard failed)
+    float lp;                        // (n1 - 1/2) - vr, n1 = G_c - (vi + pi): trigArg IS G_c iff lp < t < lp + 1,
+                                     // t = fma(phaseEst, 1/ulp, -pi) as warp 0 computes it (PLL_ROW_INVALID if a guard failed)
     int stamp;                       // (step & ~15) + 1: which block of 16 steps of the launch the table is for
 };
 
@@ -661,7 +669,7 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
     const int kbase = r.kbase, base = r.base, cnt = r.cnt;
     const unsigned in_base = r.in_base, tab_base = r.tab_base, sg_base = r.sg_base, prog_addr = r.prog_addr;
     int bad = 0, gi = r.gi, n_exact = 0;
-    float ttmax = 0.0f, fracmax = 0.0f, dmax = 0.0f;
+    float cmax = 0.0f;
     // (a, b) = t < lo ? (a0, b0) : t > hi ? (a2, b2) : (a1, b1), as selects on the data path (a predicated
     // instruction waits longer for its predicate than a select does)
     auto pick = [](float t, float lo, float hi, float a0, float a1, float a2, float b0, float b1, float b2, float &a, float &b) {
@@ -675,29 +683,31 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
             : "=&f"(a), "=&f"(b)
             : "f"(t), "f"(lo), "f"(hi), "f"(a0), "f"(a1), "f"(a2), "f"(b0), "f"(b1), "f"(b2));
     };
-    // One step: from (integrator, phaseEst) after sample u, the table of step u and {vi, vr} of
-    // sample u to the state after sample u+1 -- or, with `last`, to Kp*errorD, Ki*errorD of sample
-    // u+1 (what a block hands to the next one and to the exact fall-back).
+    // One step: from (integrator, phaseEst) after sample u and the table of step u to the state
+    // after sample u+1 -- or, with `last`, to Kp*errorD, Ki*errorD of sample u+1 (what a block hands
+    // to the next one and to the exact fall-back).
     //   - three hypotheses: trigArg(u) is grid point G_c-1, G_c, G_c+1; for each the loop filter
     //     (:163-164) of sample u+1 -- float additions that need the state but not the index;
     //   - which one: trigArg(u) is the float nearest w*trigOffset + phaseEst (:166-167), i.e. grid
     //     point vi + pi + rint(z), z = t + vr, t = fma(phaseEst, 1/ulp, -pi).  So G_c - 1 iff
-    //     z < n1 - 1/2 iff t < (n1 - 1/2) - vr, and G_c + 1 iff t > (n1 + 1/2) - vr: two compares of t
-    //     against values ready long before; two selects pick the state.
-    // On the dependent chain: one FFMA, a compare, two selects.  Everything else -- z, its
-    // rint (parked: the grid index less vi + kbase), the guards -- hangs off t beside the chain.
-    // Guards (they only accumulate; the block is stepped again the exact way if one fails):
+    //     z < n1 - 1/2 iff t < lp, and G_c + 1 iff t > lp + 1: two compares of t against values
+    //     ready long before; two selects pick the state.
+    // On the dependent chain: one FFMA, a compare, two selects.  Returns the bits of t (parked:
+    // the grid index is vi + pi + rint(t + vr)).
+    // Guards (they only accumulate; the block is stepped again the exact way if one fails), on
+    // q = t - (lp + 1/2) = z - n1 up to rounding:
     //   - the table is this block's (stamp);
-    //   - |z - n1| < 3/2: the grid point is one of the three;
-    //   - z is clear of a tie by 2^-21 * max(|t|, 4).  Error budget, in grid steps: t <= 2^-24 |t|,
-    //     vr 2^-25, the two thresholds <= 2^-24 (|n1| + 2) each, z (for this guard) <= 2^-24 (|t| + 1),
-    //     the reference's own double rounding of the sum < 2^-29; with |n1| <= |t| + 2 that is below
-    //     2^-24 (5 |t| + 9), and 2^-21 * max(|t|, 4) = 2^-24 * 8 max(|t|, 4) is above it.
-    auto step = [&](int4 ra, int4 rb, int2 vg, int stamp, bool last) -> int {
+    //   - |q| < 3/2: the grid point is one of the three;
+    //   - q is clear of +-1/2 (a tie of the float rounding) by 2^-15.  The candidate warps only
+    //     emit tables with |n1| <= 60, so |t| < 62, and the error budget in grid steps is: t
+    //     <= 2^-24 |t|, vr 2^-25, the thresholds lp, lp + 1, lp + 1/2 <= 2^-24 (|n1| + 2) each, the
+    //     reference's own double rounding of the sum < 2^-29 -- below 2^-24 * 320 < 2^-15.
+    // All three are one test: | | |q| - 1/2 | - 1/2 | < 1/2 - 2^-15.
+    auto step = [&](int4 ra, int4 rb, int stamp, bool last) -> int {
         const float kpe0 = __int_as_float(ra.x), kie0 = __int_as_float(ra.y), kpe1 = __int_as_float(ra.z), kie1 = __int_as_float(ra.w);
         const float kpe2 = __int_as_float(rb.x), kie2 = __int_as_float(rb.y);
-        const float lq = __int_as_float(rb.z), vr = __int_as_float(vg.y);
-        const float lp = p_faddf(lq, -vr), hp = p_faddf(lp, 1.0f);
+        const float lp = __int_as_float(rb.z);
+        const float hp = p_faddf(lp, 1.0f), lc = p_faddf(lp, 0.5f);
         const float tt = __fmaf_rn(ph, inv_ulp_f, -pi_f);
         if (!last) {
             const float i0 = p_faddf(integ, kie0), i1 = p_faddf(integ, kie1), i2 = p_faddf(integ, kie2);     // :163
@@ -706,19 +716,12 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
         } else {
             pick(tt, lp, hp, kpe0, kpe1, kpe2, kie0, kie1, kie2, kpe, kie);
         }
-        const float z = p_faddf(tt, vr);
-        const float zm = p_faddf(z, 12582912.0f);                     // 1.5 * 2^23: rint in the low bits
         bad |= rb.w ^ stamp;
-        dmax = fmaxf(dmax, fabsf(p_faddf(z, -p_faddf(lq, 0.5f))));
-        ttmax = fmaxf(ttmax, fabsf(tt));
-        fracmax = fmaxf(fracmax, fabsf(p_faddf(z, -p_faddf(zm, -12582912.0f))));
-        return __float_as_int(zm);
+        const float q = p_faddf(tt, -lc);
+        cmax = fmaxf(cmax, fabsf(p_faddf(fabsf(p_faddf(fabsf(q), -0.5f)), -0.5f)));
+        return __float_as_int(tt);
     };
-    // the guards of a block: the tie margin (the block's largest |t| for all of its steps), one of
-    // the three hypotheses at every step, every table this block's
-    auto guards_failed = [&]() {
-        return bad != 0 || !(dmax < 1.5f) || !(__fmaf_rn(fmaxf(ttmax, 4.0f), 0x1p-21f, fracmax) < 0.5f);
-    };
+    auto guards_failed = [&]() { return bad != 0 || !(cmax < 0.5f - 0x1p-15f); };
     auto load_vg = [&](unsigned addr) {
         int2 v;
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -745,7 +748,7 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
             gi = r.gi;
         }
         bad = 0;
-        ttmax = fracmax = dmax = 0.0f;
+        cmax = 0.0f;
         return true;
     };
     int t = 0;
@@ -765,27 +768,25 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
         const unsigned tab_a0 = tab_base + (unsigned)(u0 & (PLL_TABLES - 1)) * (unsigned)sizeof(PllRow);
         const int stamp = u0 + 1;
         int gis[16];
-        // tables and {vi, vr} are fetched two steps ahead -- late enough for the candidate warps,
-        // early enough to be off the chain; the key half of a table before its other half
+        // tables are fetched two steps ahead -- late enough for the candidate warps, early enough
+        // to be off the chain; the half of a table with the stamp before its other half
         int4 rb0 = load_half(tab_a0 + 16u), ra0 = load_half(tab_a0);
         int4 rb1 = load_half(tab_a0 + (unsigned)sizeof(PllRow) + 16u), ra1 = load_half(tab_a0 + (unsigned)sizeof(PllRow));
-        int2 vg0 = load_vg(in_a0), vg1 = load_vg(in_a0 + (unsigned)sizeof(PllIn));
+        const int2 vg_last = load_vg(in_a0 + 15u * (unsigned)sizeof(PllIn));
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             int4 rb2 = rb1, ra2 = ra1;
-            int2 vg2 = vg1;
             if (j + 2 < 16) {
                 rb2 = load_half(tab_a0 + (unsigned)(j + 2) * (unsigned)sizeof(PllRow) + 16u);
                 ra2 = load_half(tab_a0 + (unsigned)(j + 2) * (unsigned)sizeof(PllRow));
-                vg2 = load_vg(in_a0 + (unsigned)(j + 2) * (unsigned)sizeof(PllIn));
             }
-            gis[j] = step(ra0, rb0, vg0, stamp, j == 15);
-            if (j == 15)
-                gi = gis[15] + vg0.x + kbase;                         // the block's last grid index (:166-167)
-            ra0 = ra1; rb0 = rb1; vg0 = vg1;
-            ra1 = ra2; rb1 = rb2; vg1 = vg2;
+            gis[j] = step(ra0, rb0, stamp, j == 15);
+            ra0 = ra1; rb0 = rb1;
+            ra1 = ra2; rb1 = rb2;
         }
-        // park the bits of the 16 zm's for the I/O warp (every lane the same stores)
+        // the block's last grid index (:166-167): vi + pi + rint(t + vr)
+        gi = vg_last.x + kbase + __float_as_int(p_faddf(p_faddf(__int_as_float(gis[15]), __int_as_float(vg_last.y)), 12582912.0f));
+        // park the bits of the 16 t's for the I/O warp (every lane the same stores)
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(gis[j]), "r"(gis[j + 1]),
@@ -809,9 +810,9 @@ template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const
             const unsigned row = tab_base + (unsigned)(u & (PLL_TABLES - 1)) * (unsigned)sizeof(PllRow);
             const int4 rb = load_half(row + 16u), ra = load_half(row);
             const int2 vg = load_vg(in_base + (unsigned)(u & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
-            const int zb = step(ra, rb, vg, u0 + 1, j == nb - 1);
-            gi = zb + vg.x + kbase;
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(zb) : "memory");
+            const int tb = step(ra, rb, u0 + 1, j == nb - 1);
+            gi = vg.x + kbase + __float_as_int(p_faddf(p_faddf(__int_as_float(tb), __int_as_float(vg.y)), 12582912.0f));
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(tb) : "memory");
         }
         fatal = !settle(u0, nb, integ0, ph0, gi0);
     }
@@ -891,7 +892,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     if (threadIdx.x < PLL_PH_RING)
         s_ph[threadIdx.x] = make_int2(0, 0);
     for (int i = threadIdx.x; i < PLL_TABLES; i += PLL_THREADS) {
-        s_tab[i].lq = PLL_ROW_INVALID;
+        s_tab[i].lp = PLL_ROW_INVALID;
         s_tab[i].stamp = 0;
     }
     if (threadIdx.x == 0)
@@ -1084,6 +1085,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const int u = base + t8 + (live ? sq : 0);
                     const double v = s_in[u & (PLL_RING - 1)].v;
                     const int vi = s_in[u & (PLL_RING - 1)].vi;
+                    const float vr = s_in[u & (PLL_RING - 1)].vr;
                     const PllIn nx = s_in[(u + 1) & (PLL_RING - 1)];     // the sample the result is for
                     // the predictor publishes in order: once the last record of the batch is there, all are
                     const int last = min(base + t8 + PLL_BATCH - 1, base + cnt - 1);
@@ -1114,6 +1116,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     bool ok = have && ag > (1 << 23) && ag < (1 << 24);
                     const float ed = error_from_feedback(f, nx.x, nx.xd, ok);         // :159-161 of sample u+1
                     // the table is good if the guards of its three grid points held
+                    const int n1 = gc - (vi + s_kbase) - 0x4B400000;                  // G_c - (vi + pi): small
+                    ok = ok && n1 >= -60 && n1 <= 60;
                     const unsigned oks = __ballot_sync(0xffffffffu, ok || jq == 3);
                     const bool valid = ((oks >> (4 * sq)) & 7u) == 7u;
                     // the rows still hold the tables of steps u - PLL_TABLES: wait until warp 0 is past them
@@ -1129,7 +1133,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     // one store instruction writes the eight tables: 8 bytes per lane, 32 per quad
                     if (live) {
                         const int lo = jq < 3 ? __float_as_int(p_fmulf(k.kp, ed))
-                                              : __float_as_int(valid ? p_faddf((float)(gc - (vi + s_kbase) - 0x4B400000), -0.5f) : PLL_ROW_INVALID);
+                                              : __float_as_int(valid ? p_faddf(p_faddf((float)n1, -0.5f), -vr) : PLL_ROW_INVALID);
                         const int hi = jq < 3 ? __float_as_int(p_fmulf(k.ki, ed)) : (u & ~15) + 1;
                         asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(smem_u32(&s_tab[u & (PLL_TABLES - 1)]) + 8u * (unsigned)jq),
                                      "r"(lo), "r"(hi)
@@ -1185,7 +1189,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 const int pb = base - PLL_GROUP;
                 for (int j = lane + 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS)
                     tr[pb + j] = s_spec[(g - 1) & 1]
-                                     ? __double2float_rn(p_mul((double)(s_g[(g - 1) & 1][j] + s_in[(pb + j) & (PLL_RING - 1)].vi + s_kb_hist[(g - 1) & 1]),
+                                     ? __double2float_rn(p_mul((double)parked_index(s_g[(g - 1) & 1][j], s_in[(pb + j) & (PLL_RING - 1)], s_kb_hist[(g - 1) & 1]),
                                                                s_ulp_hist[(g - 1) & 1]))
                                      : __int_as_float(s_g[(g - 1) & 1][j]);
             }
@@ -1196,7 +1200,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     if (warp == 1 && n > 0) {
         const int g = (n - 1) / PLL_GROUP, pb = g * PLL_GROUP;
         for (int j = lane; pb + j < n && j < PLL_GROUP; j += 32)
-            tr[pb + j] = s_spec[g & 1] ? __double2float_rn(p_mul((double)(s_g[g & 1][j] + s_in[(pb + j) & (PLL_RING - 1)].vi + s_kb_hist[g & 1]),
+            tr[pb + j] = s_spec[g & 1] ? __double2float_rn(p_mul((double)parked_index(s_g[g & 1][j], s_in[(pb + j) & (PLL_RING - 1)], s_kb_hist[g & 1]),
                                                                  s_ulp_hist[g & 1]))
                                        : __int_as_float(s_g[g & 1][j]);
     }
