@@ -58,7 +58,6 @@ struct PllArgs {
     float *state;           // capture c at state + 8*c: integ, phase, fbI, fbQ, ncoLast, trigOffset
     PllParams prm;
     pllcore::TrigK kconst;  // filled by launch_pll: read as constant-bank operands in the loop
-    int variant;            // filled by launch_pll: which compiled form of the table-step loop runs
 };
 cudaError_t launch_pll(const PllArgs &a, int n_captures, cudaStream_t s);
 

@@ -17,7 +17,9 @@
 // the reference's exact sequence -- so one MAC costs an FMUL and an FADD: the
 // attainable ceiling of these kernels is half the FFMA peak by construction.
 #include "fmrx_internal.h"
-#include <cstdio>   // TEMP debug
+#ifdef FMRX_PLL_PROFILE   // development build: k_pll prints its cycle accounting for capture 0 of every launch
+#include <cstdio>
+#endif
 
 namespace fmrx {
 
@@ -324,15 +326,12 @@ template <int D> static cudaError_t launch_rf_demod_win(const RfDemodArgs &a, in
 cudaError_t launch_rf_demod(const RfDemodArgs &a, int n_captures, cudaStream_t s)
 {
     // the reference's modes decimate by 10, 4 and 9 (src/project.cpp:327-362)
-    static const bool ab_generic = getenv("FMRX_AB_RF_GENERIC") != nullptr;   // TEMP A/B
-    if (!ab_generic) {
     if (a.decim == 10)
         return launch_rf_demod_win<10>(a, n_captures, s);
     if (a.decim == 4)
         return launch_rf_demod_win<4>(a, n_captures, s);
     if (a.decim == 9)
         return launch_rf_demod_win<9>(a, n_captures, s);
-    }
     static size_t configured = 0;
     const size_t smem = rf_smem_bytes(a.T, a.decim);
     if (smem > configured) {
@@ -419,41 +418,50 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 // K3: PLL recurrence (src/filter.cpp:157-171)
 // ============================================================================
 // The recurrence is one dependent chain per capture, so its latency bounds the
-// throughput of the whole receive chain; fmrx_pll_core.h holds the low-latency
-// formulation of one step and the measurements behind it.  One CTA of twelve warps per
-// capture, every warp SIMT-uniform or one-lane-per-item:
+// throughput of the whole receive chain; fmrx_pll_core.h holds the exact formulation of
+// one step and the measurements behind it.  Evaluated as the reference writes it, a step
+// is a sincos, two float products, an atan2 and the loop filter in sequence: ~300 cycles
+// on this machine however it is arranged.  k_pll takes the sincos and the atan2 OFF the
+// chain by speculating on values, with one CTA of twelve warps per capture (every warp
+// SIMT-uniform or one-lane-per-item):
 //
-//   warp 0  the chain, reduced to what is irreducibly sequential: the four float
-//           operations of the loop filter, the conversion of phaseEst to double, the sum
-//           s = w*trigOffset + phaseEst, its grid index G = rint(s/ulp) -- and then a
-//           TABLE LOOKUP of the next phase-detector output.  About 95 dependent cycles.
-//   warps 2,3,5-7,9-11  value speculation.  trigArg(u) = fl32(s) lives on the float grid of
-//           its binade (spacing 2^-7 .. 0.5 rad after the first second) and a few
-//           loop-filter updates move phaseEst by far less than that, so trigArg(u) is one
-//           of a handful of grid points around rint((w*trigOffset(u) + phaseEst(u-L))/ulp).
-//           As soon as warp 0 publishes phaseEst(u-L), the 32 lanes of a candidate warp
-//           evaluate, for the 32 grid points G_c-16 .. G_c+15, everything that hangs off
-//           trigArg(u): sin/cos (Cody-Waite + two polynomials), their float roundings, the
-//           wrapped angle, the float products with pilot sample u+1, the FMA residuals and
-//           the atan2 shortcut -- i.e. errorD(u+1) = fl32(atan2(eQ, eI)) of the NEXT sample
-//           for each candidate (SIMT: the instructions of a single evaluation).  The entry
-//           warp 0 picks is bit for bit what the sequential formulation computes.
-//   warp 1  I/O.  One lane per sample: the coalesced pilot load, (double)x, the IEEE
-//           reciprocal 1/x, the half-turn flag and w*trigOffset for the group after next
-//           into a 4-group ring in shared memory; and the coalesced store of the previous
-//           group's trigArg.
+//   warp 9   the predictor.  The phase detector computes atan2(x*(-sin t), x*cos t), which
+//            up to float rounding is wrap(pi*(x < 0) - t): with that, a step of the recurrence
+//            is a handful of float operations (predictor_step), about half of what warp 0
+//            needs.  The predictor runs ahead of warp 0 (restarted from the exact state at
+//            every group of 1024 steps) and publishes its phaseEst of every step.  It is
+//            never used for a result -- it says which float trigArg(u) will almost certainly
+//            be: on a locked loop the exact trigArg is the predicted float grid point or a
+//            neighbour (tests/test_pll_model.py::test_predictor_tracks_the_exact_recurrence).
+//   warps 2,3,6,7,10,11   candidate tables.  trigArg(u) = fl32(w*trigOffset + phaseEst) lives
+//            on the float grid of its binade.  For the three grid points G_c-1, G_c, G_c+1
+//            around the predictor's, a quad of lanes evaluates everything that hangs off
+//            trigArg(u): sin/cos (Cody-Waite + two polynomials), their float roundings, the
+//            wrapped angle, the float products with pilot sample u+1, the FMA residuals and
+//            the atan2 shortcut -- i.e. Kp*errorD, Ki*errorD of the NEXT sample under each
+//            hypothesis, bit for bit what the sequential formulation computes.  Eight steps
+//            per pass of a warp; one 32-byte table (PllRow) per step.
+//   warp 0   the chain.  Per step: the loop filter of the next sample for the three
+//            hypotheses (float additions that need the state but not the index), one FFMA
+//            t = phaseEst/ulp - pi, two compares of t against the table's thresholds --
+//            which of the three grid points trigArg(u) IS -- and two selects.  ~43 cycles,
+//            bound by instruction issue, not latency.  Guards only accumulate; a block of 16
+//            steps with a failed guard (table late or not this block's, grid point not among
+//            the three, a candidate's own guard, sum too close to a rounding tie) is stepped
+//            again the exact way (pll_block_exact), and a group that cannot be completed on
+//            its grid (binade change, too many exact blocks) is redone without tables
+//            (pll_group_checked); after a failure speculation is retried with back-off.
+//   warps 1,5   I/O.  One lane per sample: the coalesced pilot load, (double)x, the IEEE
+//            reciprocal 1/x, the half-turn flag, w*trigOffset and its split on the float grid,
+//            the predictor's constant, for the group after next into a 4-group ring in shared
+//            memory; and the coalesced store of the previous group's trigArg.
+//   (warps 4, 8 share warp 0's scheduler and only take part in the barriers.)
 //
-// Hand-off is through shared memory with sequence-tagged 16-byte records written by one
-// store (phaseEst from warp 0; table headers from the candidate warps after a block
-// fence) and bounded polling -- no barrier inside a group.  Steps run in groups from a
-// register checkpoint: guards (x normal, roundings tiny, angle clear of the +-pi seam,
-// binade unchanged, grid point among the 32 candidates, table on time) only accumulate
-// into a flag, and a group with a failed guard is redone by warp 0 alone with the
-// checked/generic step; after a failure the next groups run checked directly and
-// speculation is retried with exponential back-off (the first fraction of a second of
-// a capture, where the float grid is finer than the loop's own jitter, runs checked).
-// Only trigArg leaves the chain; the NCO output cos(trigArg*scale+adjust) is evaluated
-// in K4.
+// Hand-off is through shared memory rings with sequence stamps and bounded polling: the
+// predictor's phaseEst records, the candidate tables, and one progress word warp 0 writes
+// per block (flow control for both rings; also how a group is called off).  No barrier
+// inside a group.  Only trigArg leaves the chain; the NCO output
+// cos(trigArg*scale+adjust) is evaluated in K4.
 
 constexpr int PLL_WARPS = 12;
 constexpr int PLL_THREADS = 32 * PLL_WARPS;
@@ -473,7 +481,7 @@ static_assert(PLL_TABLES % 16 == 0 && PLL_PH_RING % PLL_BATCH == 0, "no ring wra
 static_assert(PLL_PRED_LEAD + PLL_TABLES <= PLL_PH_RING, "a record outlives every candidate that may still need it");
 constexpr int PLL_ABANDONED = -1;        // progress value: warp 0 gave the group up
 constexpr int PLL_EXACT_MAX = PLL_GROUP / 128;  // exact blocks (an eighth of the group) after which a speculated group is given up
-constexpr int PLL_BACKOFF_MAX = 64;      // groups run unspeculated between retries after repeated failures
+constexpr int PLL_BACKOFF_MAX = 8;       // groups run unspeculated between retries after repeated failures
 
 struct __align__(16) PllIn {             // off-chain inputs of one sample
     float x;
@@ -661,7 +669,7 @@ struct __align__(32) PllRow {
     int stamp;                       // (step & ~15) + 1: which block of 16 steps of the launch the table is for
 };
 
-template <int V> __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
+__device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
 {
     using namespace pllcore;
     float integ = r.integ, ph = r.ph, kpe = r.kpe, kie = r.kie;
@@ -905,10 +913,11 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     bool dead = false;               // a hand-off timed out: stay on the checked path
     int backoff = 0, skip = 0;       // after a failed group: run `skip` groups checked, then retry
     int n_groups = 0, n_redone = 0, n_exact = 0;
-    long long dbg_cyc = 0, dbg_wait = 0, dbg_pre = 0, dbg_bar = 0;
-    const long long dbg_k0 = clock64();
-    const int n_groups_all = (n + PLL_GROUP - 1) / PLL_GROUP;
-    int dbg_steps = 0;
+#ifdef FMRX_PLL_PROFILE
+    long long prof_steps_cyc = 0, prof_wait = 0, prof_pre = 0;
+    const long long prof_k0 = clock64();
+    int prof_steps = 0;
+#endif
     if (warp == 0) {
         ch.integ = st[0];
         ch.ph = st[1];
@@ -934,7 +943,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         // ---- group header (warp 0) ----
         if (warp == 0) {
             ck = ch;
-            const bool spec = !(a.variant & 512) && regular && !dead && skip == 0 && ch.binade != FMRX_DISARMED &&
+            const bool spec = regular && !dead && skip == 0 && ch.binade != FMRX_DISARMED &&
                               s_prep_ulp[g & 3] == ch.ulp;
             if (lane == 0) {
                 s_flag[0] = spec;
@@ -950,7 +959,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         __syncthreads();
         const bool spec = s_flag[0] != 0;
         const double ulp = s_grid[0], inv_ulp = s_grid[1];
-        const long long dbg_ga = clock64();
+#ifdef FMRX_PLL_PROFILE
+        const long long prof_ga = clock64();
+#endif
 
         if (warp == 0) {
             // ================= the chain =================
@@ -979,8 +990,10 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 recentre();
                 // wait (bounded) for the first tables of the group; afterwards the candidate
                 // warps run ahead and a late table only clears `good`
-                const long long dbg_w0 = clock64();
-                dbg_pre += dbg_w0 - dbg_ga;
+#ifdef FMRX_PLL_PROFILE
+                const long long prof_w0 = clock64();
+                prof_pre += prof_w0 - prof_ga;
+#endif
                 {   // lane t watches table t
                     const bool need = lane < 16 && lane < cnt;           // the first block's tables
                     int spin = 0;
@@ -996,7 +1009,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                             s_flag[1] = 1;
                     }
                 }
-                dbg_wait += clock64() - dbg_w0;
+#ifdef FMRX_PLL_PROFILE
+                prof_wait += clock64() - prof_w0;
+#endif
                 // the steps themselves: a separately compiled function, so that its instruction
                 // schedule -- which IS the step time -- does not move when anything else in this
                 // kernel changes
@@ -1023,11 +1038,14 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 r.toff_base = ch.toff;
                 if (good) {
                     __syncwarp();
-                    const long long c0 = clock64();
-                    pll_table_group<0>(r, lane);
-                    const long long c1 = clock64();
-                    dbg_cyc += c1 - c0;
-                    dbg_steps += cnt;
+#ifdef FMRX_PLL_PROFILE
+                    const long long prof_c0 = clock64();
+#endif
+                    pll_table_group(r, lane);
+#ifdef FMRX_PLL_PROFILE
+                    prof_steps_cyc += clock64() - prof_c0;
+                    prof_steps += cnt;
+#endif
                     good = r.fatal == 0;
                     n_exact += r.n_exact;
                 }
@@ -1204,9 +1222,6 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                                                                  s_ulp_hist[g & 1]))
                                        : __int_as_float(s_g[g & 1][j]);
     }
-    if ((a.variant & 256) && c == 0 && (warp == 2 || warp == 11) && lane == 0)
-        printf("pll dbg cand warp %d: first round starts %.0f after the barrier and takes %.0f; second round (incl. wait) %.0f\n", warp,
-               (double)dbg_pre / n_groups_all, (double)dbg_wait / n_groups_all, dbg_steps ? (double)dbg_cyc / dbg_steps : 0.0);
     if (warp == 0 && lane == 0) {
         if (stale)
             chain_refresh(ch);
@@ -1217,11 +1232,13 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         st[2] = fi;
         st[3] = fq;
         st[5] = ch.toff;
-        if ((a.variant & 256) && c == 0)
+#ifdef FMRX_PLL_PROFILE
+        if (c == 0)
             printf("pll dbg: groups %d exact blocks %d redone %d | %.1f cyc/step over %d table steps | kernel %.1f cyc/step; per group: before wait %.0f, wait for tables %.0f, steps %.0f, rest %.0f\n",
-                   n_groups, n_exact, n_redone, dbg_steps ? (double)dbg_cyc / dbg_steps : 0.0, dbg_steps, (double)(clock64() - dbg_k0) / n,
-                   (double)dbg_pre / n_groups, (double)dbg_wait / n_groups, (double)dbg_cyc / n_groups,
-                   (double)(clock64() - dbg_k0 - dbg_pre - dbg_wait - dbg_cyc) / n_groups);
+                   n_groups, n_exact, n_redone, prof_steps ? (double)prof_steps_cyc / prof_steps : 0.0, prof_steps, (double)(clock64() - prof_k0) / n,
+                   (double)prof_pre / n_groups, (double)prof_wait / n_groups, (double)prof_steps_cyc / n_groups,
+                   (double)(clock64() - prof_k0 - prof_pre - prof_wait - prof_steps_cyc) / n_groups);
+#endif
         st[6] = (float)(n_groups + 1000 * min(n_exact, 999));     // diagnostics of the last launch
         st[7] = s_flag[1] ? -1.0f : (float)n_redone;
         if (n > 0)
@@ -1233,8 +1250,6 @@ cudaError_t launch_pll(const PllArgs &a_in, int n_captures, cudaStream_t s)
 {
     PllArgs a = a_in;
     a.kconst = pllcore::trig_constants();
-    static const int variant = getenv("FMRX_PLL_VARIANT") ? atoi(getenv("FMRX_PLL_VARIANT")) : 0;   // TEMP A/B
-    a.variant = variant;
     // The chain warp's step time is pure issue-to-issue latency, and any other CTA resident
     // on the same SM (the FIR kernels of the neighbouring chunks run concurrently on the
     // other two streams) steals issue slots and shared-memory bandwidth from it: with 301

@@ -11,7 +11,12 @@
 // 8.5 cycles, FP32 4.4, each f32<->f64 conversion 18, DSETP+select 12.  Stock
 // libdevice sin/cos fall into the Payne-Hanek slow path once |trigArg| > 105615
 // (0.9 s into a capture) and stock atan2 is a division plus a degree-19
-// polynomial: 760 cycles per sample.  Here (about 250):
+// polynomial: 760 cycles per sample.  The formulation here takes about 300 as a
+// sequential step (chain_step_spec: what k_pll falls back to), and -- the point of
+// it -- splits into a part that hangs off the previous trigArg alone (make_feedback,
+// error_from_feedback: evaluated by k_pll's candidate warps for a few hypothetical
+// trigArgs ahead of time) and the loop filter (four float additions) that k_pll's
+// warp 0 is left with:
 //
 //  * sincos: trigArg is a FLOAT (24-bit significand, |x| <= 2^24) promoted to
 //    double, so a 3-term Cody-Waite reduction with 29/29/53-bit pieces of pi/2 is
