@@ -403,7 +403,7 @@ def main_b200(args):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "launch_ms": pll_ms_step / max(1, pll_launches),
                 "share_of_step": pll_ms_step / ms_step,
-                "note": "latency-bound by construction: one dependent recurrence per capture; see pll_ns_per_sample"}
+                "note": "bound by the instruction issue of one warp per capture (one dependent recurrence per capture); see pll_ns_per_sample"}
     total_k = sum(kern.values()) / args.steps
     # FP32 issue-rate view of the FIR kernels: one MAC = FMUL + FADD (bit-exact, unfused)
     macs_rf = 2.0 * TAPS / info.rf_decim            # per IQ sample (I and Q)
