@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import assert_bits_equal
+from pll_inputs import KINDS, hostile_pilot
 
 pytestmark = pytest.mark.gpu
 
@@ -100,6 +101,25 @@ def test_pll_other_parameters(fm, port):
     o, _, os_ = port.pll(x, 114000, 240e3, 0.5, 0.3, 0.01)
     assert_bits_equal(g, o, "pll nco (rds parameters)")
     assert_bits_equal(gs, os_, "pll state (rds parameters)")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_pll_hostile_inputs_bitwise(fm, port, kind):
+    """tests/pll_inputs.py: must come out bit-identical through k_pll's exact fall-backs (block-level,
+    group-level, the reference's own statements with the library atan2)."""
+    x = hostile_pilot(kind)
+    g, gs = fm.PLL(x, 19000, 240e3, 2, 0, 0.01)
+    o, _, os_ = port.pll(x, 19000, 240e3, 2, 0, 0.01)
+    assert_bits_equal(g, o, f"pll nco ({kind})")
+    assert_bits_equal(gs, os_, f"pll state ({kind})")
+    # and again from the carried state, in pieces that are not multiples of anything
+    pieces, st_g, st_o, at = [], gs, os_, 0
+    for m in (1, 15, 16, 17, 1023, 1024, 1025, 5000):
+        ga, st_g = fm.PLL(x[at:at + m], 19000, 240e3, 2, 0, 0.01, st_g)
+        oa, _, st_o = port.pll(x[at:at + m], 19000, 240e3, 2, 0, 0.01, st_o)
+        assert_bits_equal(ga, oa, f"pll nco ({kind}, piece {m})")
+        assert_bits_equal(st_g, st_o, f"pll state ({kind}, piece {m})")
+        at += m
 
 
 def test_mixer_lr_pack_bitwise(fm, port):

@@ -13,6 +13,7 @@ import pytest
 
 import pyoracle
 from conftest import assert_bits_equal
+from pll_inputs import KINDS, hostile_pilot
 
 TAP_SETS = (51, 101, 301)
 
@@ -69,6 +70,18 @@ def test_pll_bitwise_including_saturation(port, reference):
     assert_bits_equal(pn, rn, "pll nco (saturating counter)")
     assert_bits_equal(ps, rs, "pll state (saturating counter)")
     assert ps[5] == 16777216.0
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_pll_hostile_inputs_bitwise(port, reference, kind):
+    """The inputs the GPU parity tests use against the oracle (tests/pll_inputs.py): zeros, subnormals,
+    noise, huge amplitudes -- the oracle must follow the compiled reference there too (atan2 of signed
+    zeros, float overflow in the products)."""
+    x = hostile_pilot(kind)
+    pn, _, ps = port.pll(x, 19000, 240e3, 2, 0, 0.01)
+    rn, _, rs = reference.pll(x, 19000, 240e3, 2, 0, 0.01)
+    assert_bits_equal(pn, rn, f"pll nco ({kind})")
+    assert_bits_equal(ps, rs, f"pll state ({kind})")
 
 
 @pytest.mark.parametrize("mode,taps,nblocks", [(0, 51, 40), (0, 101, 12), (0, 301, 8), (1, 51, 24),

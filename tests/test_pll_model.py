@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from conftest import assert_bits_equal
+from pll_inputs import KINDS, hostile_pilot
 
 ROOT = Path(__file__).resolve().parent.parent
 SRC = ROOT / "tests" / "pll_model.cpp"
@@ -124,3 +125,14 @@ def test_predictor_tracks_the_exact_recurrence(model, port, synth, mode, seed, p
     print("distance histogram (-8..+8):", hist.tolist())
     assert ng == len(worst)
     assert worst[1:].max() <= 2, worst[:20]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_fast_pll_bitwise_on_hostile_inputs(model, port, kind):
+    """tests/pll_inputs.py through the host build of the device step (checked fast step with the
+    generic fall-back): bit-identical to the oracle."""
+    x = hostile_pilot(kind)
+    trig, st, slow = run_model(model, x, 19000.0, 240e3, [0, 0, 1, 0, 0])
+    _, otrig, ost = port.pll(x, 19000, 240e3, 2, 0, 0.01)
+    assert_bits_equal(trig, otrig, f"trigArg ({kind})")
+    assert_bits_equal(st[:2], ost[:2], f"integrator, phaseEst ({kind})")
