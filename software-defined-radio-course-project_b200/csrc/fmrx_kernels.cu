@@ -540,12 +540,23 @@ __device__ __forceinline__ int parked_index(int t_bits, const PllIn &in, int kba
     return in.vi + kbase + __float_as_int(__fadd_rn(__fadd_rn(__int_as_float(t_bits), in.vr), 12582912.0f));
 }
 
+// pi of a block of 16 steps: rint(phaseEst/ulp) of the phaseEst the block starts from -- the exact one
+// at the start of a group, the predictor's thereafter (any integer near phaseEst/ulp will do: it only
+// keeps t = phaseEst/ulp - pi small; warp 0 and the candidate warps just have to use the same one).
+__device__ __forceinline__ void block_pi(float ph, float inv_ulp_f, float &pi_f, int &kbase)
+{
+    const float pm = __fadd_rn(__fmul_rn(ph, inv_ulp_f), 12582912.0f);       // rint via 1.5 * 2^23
+    pi_f = __fadd_rn(pm, -12582912.0f);
+    kbase = __float_as_int(pm) - 0x4B400000 - 0x4B400000;
+}
+
 struct TableRun {
     float integ, ph, kpe, kie;       // in/out: loop filter state; Kp*errorD, Ki*errorD of the sample about to run
-    float inv_ulp_f, pi_f;           // 1/ulp (a power of two); rint(phaseEst/ulp) at the group start
-    int kbase;                       // the same rint as an integer, less the bit pattern of 1.5 * 2^23: grid index = bits(zm) + vi + kbase
+    float inv_ulp_f, pi_f;           // 1/ulp (a power of two); pi of the group's first block
+    int kbase;                       // pi as an integer, less the bit pattern of 1.5 * 2^23 (of the block at hand, for pll_block_exact)
     int base, cnt;                   // first step and number of steps of the group
     unsigned in_base, tab_base, sg_base, prog_addr;   // shared-window addresses: ring {vi, vr}, tables, parked indices, progress word
+    unsigned sph_base, kb_base;      // ... the predictor's records, the per-block kbase of the group (for the I/O warp)
     int gi;                          // in: grid index of the trigArg before the group; out: of the last one
     int n_exact;                     // out: blocks of 16 that had to be stepped the exact way
     int fatal;                       // out: a block could not be completed here; the caller redoes the group
@@ -673,8 +684,11 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
 {
     using namespace pllcore;
     float integ = r.integ, ph = r.ph, kpe = r.kpe, kie = r.kie;
-    const float inv_ulp_f = r.inv_ulp_f, pi_f = r.pi_f;
-    const int kbase = r.kbase, base = r.base, cnt = r.cnt;
+    const float inv_ulp_f = r.inv_ulp_f;
+    float pi_f = r.pi_f;
+    int kbase = r.kbase;
+    const int base = r.base, cnt = r.cnt;
+    const unsigned sph_base = r.sph_base, kb_base = r.kb_base;
     const unsigned in_base = r.in_base, tab_base = r.tab_base, sg_base = r.sg_base, prog_addr = r.prog_addr;
     int bad = 0, gi = r.gi, n_exact = 0;
     float cmax = 0.0f;
@@ -743,6 +757,7 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
     // after a block: if a guard failed in it, the same block again, the exact way (rare)
     auto settle = [&](int u0, int nb, float integ0, float ph0, int gi0) -> bool {
         if (guards_failed()) {
+            r.kbase = kbase;
             r.integ = integ0;            // by value through r: nothing on the chain has its address taken
             r.ph = ph0;
             r.gi = gi0;
@@ -759,11 +774,31 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
         cmax = 0.0f;
         return true;
     };
+    auto load_rec = [&](int u) {      // the predictor's record of step u: {phaseEst, u + 1}
+        int2 v;
+        asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sph_base + (unsigned)(u & (PLL_PH_RING - 1)) * 8u) : "memory");
+        return v;
+    };
+    // pi of the block starting at step u0 > base: from the predictor's phaseEst of step u0 - 1.  The
+    // record is fetched and turned into (pi, kbase) in the middle of the block before, beside the
+    // chain.  No branch at the block boundary: if the record was not there yet (or is out of range)
+    // the block keeps the previous pi and fails its guards.
+    float pi_next = 0.0f;
+    int kbase_next = 0, seq_next = 0;
+    auto next_pi = [&](int u0) {
+        const bool have = seq_next == u0 && fabsf(pi_next) < 2097152.0f;
+        pi_f = have ? pi_next : pi_f;
+        kbase = have ? kbase_next : kbase;
+        bad |= (int)!have;
+    };
     int t = 0;
     bool fatal = false;
     const int n_full = cnt >> 4;
     for (int b = 0; b < n_full; b++, t += 16) {
         const int u0 = base + t;
+        if (b > 0)
+            next_pi(u0);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(kb_base + 4u * (unsigned)(t >> 4)), "r"(kbase) : "memory");
         // the state before the block (after sample u0-1, with Kp*errorD, Ki*errorD of sample u0
         // pending), in case it has to be stepped the exact way
         const float integ0 = integ, ph0 = ph;
@@ -791,6 +826,11 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
             gis[j] = step(ra0, rb0, stamp, j == 15);
             ra0 = ra1; rb0 = rb1;
             ra1 = ra2; rb1 = rb2;
+            if (j == 8) {            // the next block's pi (the predictor is normally far enough ahead by now)
+                const int2 rec = load_rec(u0 + 15);
+                block_pi(__int_as_float(rec.x), inv_ulp_f, pi_next, kbase_next);
+                seq_next = rec.y;
+            }
         }
         // the block's last grid index (:166-167): vi + pi + rint(t + vr)
         gi = vg_last.x + kbase + __float_as_int(p_faddf(p_faddf(__int_as_float(gis[15]), __int_as_float(vg_last.y)), 12582912.0f));
@@ -809,6 +849,9 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
     }
     if (!fatal && t < cnt) {     // the short last block of a launch
         const int u0 = base + t, nb = cnt - t;
+        if (t > 0)
+            next_pi(u0);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(kb_base + 4u * (unsigned)(t >> 4)), "r"(kbase) : "memory");
         const float integ0 = integ, ph0 = ph;
         const int gi0 = gi;
         integ = p_faddf(integ, kie);
@@ -841,7 +884,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     __shared__ __align__(16) int2 s_ph[PLL_PH_RING];  // {predicted phaseEst, step + 1}, written by the predictor warp
     __shared__ float s_hdr[2];                        // integrator, phaseEst at the start of the group (warp 0 -> predictor)
     __shared__ int s_kbase;                           // rint(phaseEst/ulp) at the start of the group, less the bits of 1.5 * 2^23
-    __shared__ int s_kb_hist[2];                      // ... of the group whose parked values are in s_g[.]
+    __shared__ int s_kb_blk[2][PLL_GROUP / 16];       // kbase of every block of the group whose parked values are in s_g[.]
     __shared__ int s_prog;                            // steps of the capture warp 0 has completed (per block of 16), or PLL_ABANDONED
     __shared__ PllRow s_tab[PLL_TABLES];              // candidate tables, a ring over the steps
     __shared__ __align__(16) int s_g[2][PLL_GROUP];                 // grid index of each trigArg of the group, double-buffered
@@ -1029,6 +1072,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 r.tab_base = smem_u32(&s_tab[0]);
                 r.sg_base = smem_u32(&s_g[g & 1][0]);
                 r.prog_addr = smem_u32(&s_prog);
+                r.sph_base = smem_u32(&s_ph[0]);
+                r.kb_base = smem_u32(&s_kb_blk[g & 1][0]);
                 r.gi = __double2int_rn(p_mul(ch.tad, inv_ulp));                  // exact: trigArg is on the grid
                 r.n_exact = 0;
                 r.fatal = 0;
@@ -1083,7 +1128,6 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             if (lane == 0) {
                 s_spec[g & 1] = good ? 1 : 0;
                 s_ulp_hist[g & 1] = ulp;
-                s_kb_hist[g & 1] = s_kbase;
             }
         } else if (role >= 2) {
             // ================= candidate tables =================
@@ -1122,8 +1166,18 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                         break;
                     }
                     const int2 pr = ld_v2(&s_ph[u & (PLL_PH_RING - 1)]);
+                    // pi of the block these eight steps belong to: as warp 0 takes it
+                    const int ub = (base + t8) & ~15;
+                    int kb = s_kbase;
+                    bool have_pi = true;
+                    if (ub != base) {
+                        const int2 rb = ld_v2(&s_ph[(ub - 1) & (PLL_PH_RING - 1)]);
+                        float pif;
+                        block_pi(__int_as_float(rb.x), (float)inv_ulp, pif, kb);
+                        have_pi = rb.y == ub;
+                    }
                     // (a record that is not this step's: the warp fell a whole ring behind -- no table then)
-                    const bool have = pr.y == u + 1;
+                    const bool have = pr.y == u + 1 && have_pi;
                     // this lane's grid point: G_c - 1 + j
                     const int gc = grid_index(grid_round(p_add(v, (double)__int_as_float(pr.x)), inv_ulp));
                     const int gl = gc - 1 + jq;
@@ -1134,7 +1188,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     bool ok = have && ag > (1 << 23) && ag < (1 << 24);
                     const float ed = error_from_feedback(f, nx.x, nx.xd, ok);         // :159-161 of sample u+1
                     // the table is good if the guards of its three grid points held
-                    const int n1 = gc - (vi + s_kbase) - 0x4B400000;                  // G_c - (vi + pi): small
+                    const int n1 = gc - (vi + kb) - 0x4B400000;                       // G_c - (vi + pi): small
                     ok = ok && n1 >= -60 && n1 <= 60;
                     const unsigned oks = __ballot_sync(0xffffffffu, ok || jq == 3);
                     const bool valid = ((oks >> (4 * sq)) & 7u) == 7u;
@@ -1207,7 +1261,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 const int pb = base - PLL_GROUP;
                 for (int j = lane + 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS)
                     tr[pb + j] = s_spec[(g - 1) & 1]
-                                     ? __double2float_rn(p_mul((double)parked_index(s_g[(g - 1) & 1][j], s_in[(pb + j) & (PLL_RING - 1)], s_kb_hist[(g - 1) & 1]),
+                                     ? __double2float_rn(p_mul((double)parked_index(s_g[(g - 1) & 1][j], s_in[(pb + j) & (PLL_RING - 1)], s_kb_blk[(g - 1) & 1][j >> 4]),
                                                                s_ulp_hist[(g - 1) & 1]))
                                      : __int_as_float(s_g[(g - 1) & 1][j]);
             }
@@ -1218,7 +1272,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     if (warp == 1 && n > 0) {
         const int g = (n - 1) / PLL_GROUP, pb = g * PLL_GROUP;
         for (int j = lane; pb + j < n && j < PLL_GROUP; j += 32)
-            tr[pb + j] = s_spec[g & 1] ? __double2float_rn(p_mul((double)parked_index(s_g[g & 1][j], s_in[(pb + j) & (PLL_RING - 1)], s_kb_hist[g & 1]),
+            tr[pb + j] = s_spec[g & 1] ? __double2float_rn(p_mul((double)parked_index(s_g[g & 1][j], s_in[(pb + j) & (PLL_RING - 1)], s_kb_blk[g & 1][j >> 4]),
                                                                  s_ulp_hist[g & 1]))
                                        : __int_as_float(s_g[g & 1][j]);
     }
