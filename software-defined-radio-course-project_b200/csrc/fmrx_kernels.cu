@@ -475,6 +475,8 @@ constexpr int PLL_RING = 4 * PLL_GROUP;  // per-sample input ring: 4 groups
 constexpr int kPllSpareSms = 32;         // SMs that must stay free for the FIR kernels before PLL CTAs claim whole SMs
 constexpr int PLL_TABLES = 128;          // candidate tables in flight (a ring over the steps)
 constexpr int PLL_PH_RING = 256;         // predicted-phaseEst records in flight
+constexpr int PLL_HEAD = 48;             // steps of the NEXT group the predictor and the candidate warps do at the end of a group,
+                                         // so that warp 0 finds its first tables waiting (multiple of 16)
 constexpr int PLL_PRED_LEAD = 128;       // the predictor stays at most this far ahead of warp 0
 constexpr int PLL_SPIN_LIMIT = 1 << 16;  // bounded polling (~1 ms): a bug must not hang the GPU
 static_assert(PLL_TABLES % 16 == 0 && PLL_PH_RING % PLL_BATCH == 0, "no ring wraps inside a block of 16 steps or a batch of candidates");
@@ -557,6 +559,7 @@ struct TableRun {
     int base, cnt;                   // first step and number of steps of the group
     unsigned in_base, tab_base, sg_base, prog_addr;   // shared-window addresses: ring {vi, vr}, tables, parked indices, progress word
     unsigned sph_base, kb_base;      // ... the predictor's records, the per-block kbase of the group (for the I/O warp)
+    int cont;                        // the group continues the one before: pi of its first block comes from the predictor too
     int gi;                          // in: grid index of the trigArg before the group; out: of the last one
     int n_exact;                     // out: blocks of 16 that had to be stepped the exact way
     int fatal;                       // out: a block could not be completed here; the caller redoes the group
@@ -794,9 +797,14 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
     int t = 0;
     bool fatal = false;
     const int n_full = cnt >> 4;
+    if (r.cont) {        // (once per group: this one may wait for the load)
+        const int2 rec = load_rec(base - 1);
+        block_pi(__int_as_float(rec.x), inv_ulp_f, pi_next, kbase_next);
+        seq_next = rec.y;
+    }
     for (int b = 0; b < n_full; b++, t += 16) {
         const int u0 = base + t;
-        if (b > 0)
+        if (b > 0 || r.cont)
             next_pi(u0);
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(kb_base + 4u * (unsigned)(t >> 4)), "r"(kbase) : "memory");
         // the state before the block (after sample u0-1, with Kp*errorD, Ki*errorD of sample u0
@@ -849,7 +857,7 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
     }
     if (!fatal && t < cnt) {     // the short last block of a launch
         const int u0 = base + t, nb = cnt - t;
-        if (t > 0)
+        if (t > 0 || r.cont)
             next_pi(u0);
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(kb_base + 4u * (unsigned)(t >> 4)), "r"(kbase) : "memory");
         const float integ0 = integ, ph0 = ph;
@@ -892,7 +900,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     __shared__ double s_prep_ulp[4];                  // ulp the ring slots of each group were prepared with
     __shared__ double s_ulp_hist[2];                  // ulp the parked grid indices of a group refer to
     __shared__ int s_spec[2];                         // 1: s_g holds grid indices, 0: float bit patterns
-    __shared__ int s_flag[4];                         // [0] group runs speculatively, [1] error, [2] the next group's slots are stale
+    __shared__ int s_flag[4];                         // [0] group runs speculatively, [1] error, [2] the next group's slots are stale,
+                                                      // [3] the group continues the one before (its head is already done)
 
     const int c = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -956,6 +965,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     bool dead = false;               // a hand-off timed out: stay on the checked path
     int backoff = 0, skip = 0;       // after a failed group: run `skip` groups checked, then retry
     int n_groups = 0, n_redone = 0, n_exact = 0;
+    float pred_integ = 0.0f, pred_ph = 0.0f;          // the predictor's state (warp 9)
 #ifdef FMRX_PLL_PROFILE
     long long prof_steps_cyc = 0, prof_wait = 0, prof_pre = 0;
     const long long prof_k0 = clock64();
@@ -993,6 +1003,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 s_grid[0] = ch.ulp;
                 s_grid[1] = ch.inv_ulp;
                 s_flag[2] = s_prep_ulp[(g + 1) & 3] != ch.ulp;
+                s_flag[3] = spec && have_ed;         // the group before ran on tables to its end: predictor and candidates did our head
                 s_kbase = __float_as_int(p_faddf(p_fmulf(ch.ph, (float)ch.inv_ulp), 12582912.0f)) - 0x4B400000 - 0x4B400000;
                 s_hdr[0] = ch.integ;
                 s_hdr[1] = ch.ph;
@@ -1074,6 +1085,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 r.prog_addr = smem_u32(&s_prog);
                 r.sph_base = smem_u32(&s_ph[0]);
                 r.kb_base = smem_u32(&s_kb_blk[g & 1][0]);
+                r.cont = s_flag[3];
                 r.gi = __double2int_rn(p_mul(ch.tad, inv_ulp));                  // exact: trigArg is on the grid
                 r.n_exact = 0;
                 r.fatal = 0;
@@ -1142,15 +1154,22 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(prog_a) : "memory");
                     return v;
                 };
-                for (int t8 = PLL_BATCH * cand_id; t8 < cnt; t8 += PLL_BATCH * PLL_CAND_WARPS) {
-                    const bool live = t8 + sq < cnt;
-                    const int u = base + t8 + (live ? sq : 0);
+                // steps [first, end): this group's (less its head if the group before did it) and the head
+                // of the next one; batch q = step / 8 belongs to warp q mod PLL_CAND_WARPS
+                const bool cont = s_flag[3] != 0;
+                const int first = base + (cont ? PLL_HEAD : 0);
+                const int end = base + cnt + (base + cnt + PLL_HEAD <= n ? PLL_HEAD : 0);
+                const int q0 = first / PLL_BATCH;
+                for (int ub8 = first + ((cand_id - q0 % PLL_CAND_WARPS + PLL_CAND_WARPS) % PLL_CAND_WARPS) * PLL_BATCH; ub8 < end;
+                     ub8 += PLL_BATCH * PLL_CAND_WARPS) {
+                    const bool live = ub8 + sq < end;
+                    const int u = ub8 + (live ? sq : 0);
                     const double v = s_in[u & (PLL_RING - 1)].v;
                     const int vi = s_in[u & (PLL_RING - 1)].vi;
                     const float vr = s_in[u & (PLL_RING - 1)].vr;
                     const PllIn nx = s_in[(u + 1) & (PLL_RING - 1)];     // the sample the result is for
                     // the predictor publishes in order: once the last record of the batch is there, all are
-                    const int last = min(base + t8 + PLL_BATCH - 1, base + cnt - 1);
+                    const int last = min(ub8 + PLL_BATCH - 1, end - 1);
                     int prog = 0, spin = 0;
                     for (;; spin++) {
                         const int seq = ld_v2(&s_ph[last & (PLL_PH_RING - 1)]).y;
@@ -1167,10 +1186,10 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     }
                     const int2 pr = ld_v2(&s_ph[u & (PLL_PH_RING - 1)]);
                     // pi of the block these eight steps belong to: as warp 0 takes it
-                    const int ub = (base + t8) & ~15;
+                    const int ub = ub8 & ~15;
                     int kb = s_kbase;
                     bool have_pi = true;
-                    if (ub != base) {
+                    if (ub != base || cont) {
                         const int2 rb = ld_v2(&s_ph[(ub - 1) & (PLL_PH_RING - 1)]);
                         float pif;
                         block_pi(__int_as_float(rb.x), (float)inv_ulp, pif, kb);
@@ -1193,7 +1212,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const unsigned oks = __ballot_sync(0xffffffffu, ok || jq == 3);
                     const bool valid = ((oks >> (4 * sq)) & 7u) == 7u;
                     // the rows still hold the tables of steps u - PLL_TABLES: wait until warp 0 is past them
-                    for (spin = 0; (prog = progress()) != PLL_ABANDONED && prog - (base + t8 + PLL_BATCH - PLL_TABLES) < 0 && spin < PLL_SPIN_LIMIT;
+                    for (spin = 0; (prog = progress()) != PLL_ABANDONED && prog - (ub8 + PLL_BATCH - PLL_TABLES) < 0 && spin < PLL_SPIN_LIMIT;
                          spin++)
                         ;
                     if (prog == PLL_ABANDONED)
@@ -1221,12 +1240,20 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             // stays within a grid step or two of the exact one for the whole group (it restarts
             // from the exact state at every group).  It is only ever used to CENTRE the tables.
             if (spec) {
-                float integ = s_hdr[0], ph = s_hdr[1];
+                // a group that continues the one before finds its head done and the predictor's state
+                // where that left it (it needs no restart: tests/test_pll_model.py runs it for 20 s)
+                const bool cont = s_flag[3] != 0;
+                if (!cont) {
+                    pred_integ = s_hdr[0];
+                    pred_ph = s_hdr[1];
+                }
+                float integ = pred_integ, ph = pred_ph;
                 const unsigned prog_a = smem_u32(&s_prog);
                 const unsigned ph_a = smem_u32(&s_ph[0]);
                 const unsigned c_a = smem_u32(&s_in[0]) + 40u;                   // offset of c in a slot
                 int prog = base;
-                for (int t = 0; t < cnt; t += 16) {
+                const int t_end = cnt + (base + cnt + PLL_HEAD <= n ? PLL_HEAD : 0);
+                for (int t = cont ? PLL_HEAD : 0; t < t_end; t += 16) {
                     const int u0 = base + t;
                     int spin = 0;                // stay within PLL_PRED_LEAD of warp 0
                     do {
@@ -1249,6 +1276,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                                      : "memory");
                     }
                 }
+                pred_integ = integ;
+                pred_ph = ph;
             }
         } else if (role == 1 && io_id < PLL_IO_WARPS) {
             // ================= I/O =================
