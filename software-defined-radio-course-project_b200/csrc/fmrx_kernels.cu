@@ -801,11 +801,14 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
         const int2 rec = load_rec(base - 1);
         block_pi(__int_as_float(rec.x), inv_ulp_f, pi_next, kbase_next);
         seq_next = rec.y;
+    } else {             // the first block of a group that starts afresh: pi from the exact phaseEst (header)
+        pi_next = pi_f;
+        kbase_next = kbase;
+        seq_next = base;
     }
     for (int b = 0; b < n_full; b++, t += 16) {
         const int u0 = base + t;
-        if (b > 0 || r.cont)
-            next_pi(u0);
+        next_pi(u0);
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(kb_base + 4u * (unsigned)(t >> 4)), "r"(kbase) : "memory");
         // the state before the block (after sample u0-1, with Kp*errorD, Ki*errorD of sample u0
         // pending), in case it has to be stepped the exact way
@@ -857,8 +860,7 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
     }
     if (!fatal && t < cnt) {     // the short last block of a launch
         const int u0 = base + t, nb = cnt - t;
-        if (t > 0 || r.cont)
-            next_pi(u0);
+        next_pi(u0);
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(kb_base + 4u * (unsigned)(t >> 4)), "r"(kbase) : "memory");
         const float integ0 = integ, ph0 = ph;
         const int gi0 = gi;
