@@ -302,6 +302,7 @@ struct fmrx_pipeline {
     fmrx_mode_info mi{};
     int C = 0, device = 0;
     int chunk_blocks = 0;       // blocks per chunk
+    bool ramp = false;          // automatic chunk size: the first two chunks of a call are a quarter and a half of it
     int chunk_if = 0;           // IF samples per chunk per capture
     int H = 0;                  // IF history kept in front of every IF-rate buffer
     int hist_pairs = 0;         // IQ pairs of history for K1
@@ -396,11 +397,14 @@ int create_impl(fmrx_pipeline *p, const fmrx_config *cfg)
 
     int cb = cfg->chunk_blocks;
     if (cb <= 0) {
-        // aim at ~32 MiB per IF-rate array per chunk
-        const size_t target_if = (32u << 20) / sizeof(float) / C;
+        // aim at ~128 MiB per IF-rate array per chunk: a K3 launch has to wait for whole SMs to drain
+        // of the FIR CTAs of the neighbouring chunks (its CTAs claim a whole SM each), a third of a
+        // millisecond that is 12 % of a launch at 32 MiB and 3 % at 128
+        const size_t target_if = (128u << 20) / sizeof(float) / C;
         cb = static_cast<int>(std::max<size_t>(1, target_if / mi.if_per_block));
         cb = std::min(cb, 4096);
     }
+    p->ramp = cfg->chunk_blocks <= 0;
     p->chunk_blocks = cb;
     p->chunk_if = cb * mi.if_per_block;
     p->if_stride = static_cast<size_t>(p->H) + p->chunk_if;
@@ -516,7 +520,20 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
         CU(cudaStreamWaitEvent(p->s_back, p->ev_in, 0));
     }
 
-    const size_t n_chunks = (n_blocks + p->chunk_blocks - 1) / p->chunk_blocks;
+    // chunk sizes: with the automatic size a quarter and a half chunk first, so that the pipeline
+    // (and, from the host, the first H2D copy) fills quickly
+    std::vector<int> chunk_nb;
+    for (size_t done = 0; done < n_blocks;) {
+        int want = p->chunk_blocks;
+        if (p->ramp && chunk_nb.size() == 0)
+            want = std::max(1, p->chunk_blocks / 4);
+        else if (p->ramp && chunk_nb.size() == 1)
+            want = std::max(1, p->chunk_blocks / 2);
+        const int nb = static_cast<int>(std::min<size_t>(want, n_blocks - done));
+        chunk_nb.push_back(nb);
+        done += nb;
+    }
+    const size_t n_chunks = chunk_nb.size();
     if (p->timing) {
         while (p->tev.size() < 8 * n_chunks) {
             cudaEvent_t e;
@@ -525,9 +542,11 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
         }
     }
 
+    size_t b_next = 0;
     for (size_t ci = 0; ci < n_chunks; ci++) {
-        const size_t b0 = ci * p->chunk_blocks;
-        const int nb = static_cast<int>(std::min<size_t>(p->chunk_blocks, n_blocks - b0));
+        const size_t b0 = b_next;
+        const int nb = chunk_nb[ci];
+        b_next += nb;
         const int n_if = nb * mi.if_per_block;
         const size_t chunk_bytes = static_cast<size_t>(nb) * mi.block_size;
         const size_t chunk_pcm = static_cast<size_t>(nb) * 2 * mi.audio_per_block;

@@ -560,6 +560,9 @@ struct TableRun {
     unsigned in_base, tab_base, sg_base, prog_addr;   // shared-window addresses: ring {vi, vr}, tables, parked indices, progress word
     unsigned sph_base, kb_base;      // ... the predictor's records, the per-block kbase of the group (for the I/O warp)
     int cont;                        // the group continues the one before: pi of its first block comes from the predictor too
+#ifdef FMRX_PLL_PROFILE
+    int prof_stamp, prof_c, prof_fatal_exact;
+#endif
     int gi;                          // in: grid index of the trigArg before the group; out: of the last one
     int n_exact;                     // out: blocks of 16 that had to be stepped the exact way
     int fatal;                       // out: a block could not be completed here; the caller redoes the group
@@ -760,13 +763,24 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
     // after a block: if a guard failed in it, the same block again, the exact way (rare)
     auto settle = [&](int u0, int nb, float integ0, float ph0, int gi0) -> bool {
         if (guards_failed()) {
+#ifdef FMRX_PLL_PROFILE
+            r.prof_stamp += bad != 0;
+            r.prof_c += bad == 0;
+#endif
             r.kbase = kbase;
             r.integ = integ0;            // by value through r: nothing on the chain has its address taken
             r.ph = ph0;
             r.gi = gi0;
             n_exact++;
-            if (!pll_block_exact(r, u0, nb, lane))
+            if (!pll_block_exact(r, u0, nb, lane)) {
+#ifdef FMRX_PLL_PROFILE
+                r.prof_fatal_exact++;
+                if (blockIdx.x == 0 && lane == 0)
+                    printf("pll dbg fatal: group base %d block at %d (of %d) gi %d kbase %d\n", base, u0 - base, cnt, r.gi, r.kbase);
+                __syncwarp();
+#endif
                 return false;
+            }
             integ = r.integ;
             ph = r.ph;
             kpe = r.kpe;
@@ -971,7 +985,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
 #ifdef FMRX_PLL_PROFILE
     long long prof_steps_cyc = 0, prof_wait = 0, prof_pre = 0;
     const long long prof_k0 = clock64();
-    int prof_steps = 0;
+    int prof_steps = 0, prof_n_stamp = 0, prof_n_c = 0, prof_n_fe = 0, prof_n_fm = 0;
 #endif
     if (warp == 0) {
         ch.integ = st[0];
@@ -1088,6 +1102,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 r.sph_base = smem_u32(&s_ph[0]);
                 r.kb_base = smem_u32(&s_kb_blk[g & 1][0]);
                 r.cont = s_flag[3];
+#ifdef FMRX_PLL_PROFILE
+                r.prof_stamp = r.prof_c = r.prof_fatal_exact = 0;
+#endif
                 r.gi = __double2int_rn(p_mul(ch.tad, inv_ulp));                  // exact: trigArg is on the grid
                 r.n_exact = 0;
                 r.fatal = 0;
@@ -1104,6 +1121,10 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
 #ifdef FMRX_PLL_PROFILE
                     prof_steps_cyc += clock64() - prof_c0;
                     prof_steps += cnt;
+                    prof_n_stamp += r.prof_stamp;
+                    prof_n_c += r.prof_c;
+                    prof_n_fe += r.prof_fatal_exact;
+                    prof_n_fm += r.fatal && !r.prof_fatal_exact;
 #endif
                     good = r.fatal == 0;
                     n_exact += r.n_exact;
@@ -1319,8 +1340,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         st[5] = ch.toff;
 #ifdef FMRX_PLL_PROFILE
         if (c == 0)
-            printf("pll dbg: groups %d exact blocks %d redone %d | %.1f cyc/step over %d table steps | kernel %.1f cyc/step; per group: before wait %.0f, wait for tables %.0f, steps %.0f, rest %.0f\n",
-                   n_groups, n_exact, n_redone, prof_steps ? (double)prof_steps_cyc / prof_steps : 0.0, prof_steps, (double)(clock64() - prof_k0) / n,
+            printf("pll dbg: groups %d exact blocks %d (stamp/pi %d, guard %d) redone %d (exact step left the grid %d, too many exact blocks %d) | %.1f cyc/step over %d table steps | kernel %.1f cyc/step; per group: before wait %.0f, wait for tables %.0f, steps %.0f, rest %.0f\n",
+                   n_groups, n_exact, prof_n_stamp, prof_n_c, n_redone, prof_n_fe, prof_n_fm, prof_steps ? (double)prof_steps_cyc / prof_steps : 0.0, prof_steps, (double)(clock64() - prof_k0) / n,
                    (double)prof_pre / n_groups, (double)prof_wait / n_groups, (double)prof_steps_cyc / n_groups,
                    (double)(clock64() - prof_k0 - prof_pre - prof_wait - prof_steps_cyc) / n_groups);
 #endif
