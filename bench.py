@@ -303,6 +303,7 @@ def main_b200(args):
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
+        t_host0 = time.perf_counter()
         step_device()
         # per-kernel device times of this step (event reads only; the pipeline call above
         # already made `stream` wait for the step, so this does not add work to the region)
@@ -310,7 +311,13 @@ def main_b200(args):
         t = pipe.last_timing()
         for k_ in kern:
             kern[k_] += t[k_]
+        if world > 1:                                    # per-rank step time, for diagnosing a slow rank
+            print(f"[bench rank {rank}] device step {time.perf_counter() - t_host0:.3f} s (k_pll {t['pll_ms']:.0f} ms)",
+                  file=sys.stderr, flush=True)
+    t_host0 = time.perf_counter()
     drain()                                              # the last gather is inside the timed region
+    if world > 1:
+        print(f"[bench rank {rank}] last gather {time.perf_counter() - t_host0:.3f} s", file=sys.stderr, flush=True)
     e1.record(stream)
     torch.cuda.synchronize()
     barrier()

@@ -980,7 +980,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     float kpe_next = 0.0f, kie_next = 0.0f;
     bool dead = false;               // a hand-off timed out: stay on the checked path
     int backoff = 0, skip = 0;       // after a failed group: run `skip` groups checked, then retry
-    int n_groups = 0, n_redone = 0, n_exact = 0;
+    int n_groups = 0, n_redone = 0, n_exact = 0, prev_exact = 0;
     float pred_integ = 0.0f, pred_ph = 0.0f;          // the predictor's state (warp 9)
 #ifdef FMRX_PLL_PROFILE
     long long prof_steps_cyc = 0, prof_wait = 0, prof_pre = 0;
@@ -1019,7 +1019,10 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 s_grid[0] = ch.ulp;
                 s_grid[1] = ch.inv_ulp;
                 s_flag[2] = s_prep_ulp[(g + 1) & 3] != ch.ulp;
-                s_flag[3] = spec && have_ed;         // the group before ran on tables to its end: predictor and candidates did our head
+                // the group before ran on tables to its end and hardly needed the exact step: predictor and
+                // candidates did our head, and the predictor carries on from its own state (otherwise it
+                // restarts from the exact one: it may have drifted)
+                s_flag[3] = spec && have_ed && prev_exact <= 2;
                 s_kbase = __float_as_int(p_faddf(p_fmulf(ch.ph, (float)ch.inv_ulp), 12582912.0f)) - 0x4B400000 - 0x4B400000;
                 s_hdr[0] = ch.integ;
                 s_hdr[1] = ch.ph;
@@ -1128,6 +1131,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
 #endif
                     good = r.fatal == 0;
                     n_exact += r.n_exact;
+                    prev_exact = r.n_exact;
                 }
                 if (good) {
                     ch.integ = r.integ;

@@ -8,7 +8,7 @@ Signal model, at fs = rf_fs:
     I = cos phi + sigma n_I,  Q = sin phi + sigma n_Q,   sigma = 0.01
     u8 = clip(rint(x*100 + 128), 0, 255),  interleaved I,Q
 
-Station k of a batch uses seed=k, f_L = 1000+37k Hz, f_R = 3000+53k Hz.
+Station k of a batch uses seed=k, f_L = 1000+37(k mod 64) Hz, f_R = 3000+53(k mod 64) Hz.
 
 `synth_iq` is the numpy (host) generator used by the parity tests and the
 golden fixtures; `synth_iq_torch` produces the same signal model on a CUDA
@@ -24,6 +24,12 @@ DEVIATION_HZ = 75000.0
 
 
 def station_tones(k: int) -> tuple[float, float]:
+    """Audio tones of station k.  Stations 0..63 are SURVEY 8(d)'s batch; beyond that (multi-GPU
+    batches) the tone pair repeats with period 64 -- only the noise differs -- because 1000 + 37 k and
+    3000 + 53 k would leave the 15 kHz audio band of FM broadcast from k ~ 230 on and then sit on
+    the 19 kHz pilot itself: not an FM-stereo signal any more (the reference's PLL locks onto the
+    tone instead of the pilot)."""
+    k %= 64
     return 1000.0 + 37.0 * k, 3000.0 + 53.0 * k
 
 
