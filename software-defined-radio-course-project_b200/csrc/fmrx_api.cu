@@ -295,6 +295,8 @@ struct BufferSet {
     int16_t *pcm = nullptr;     // host-path staging: [C][chunk_blocks*2*audio_per_block]
     cudaEvent_t front_done = nullptr, pll_done = nullptr, free_ev = nullptr;
     bool free_pending = false;  // free_ev has been recorded at least once
+    cudaEvent_t h2d_done = nullptr, iq_free = nullptr;   // host path: staging filled / staging read for the last time
+    bool iq_free_pending = false;
 };
 }  // namespace
 
@@ -316,6 +318,7 @@ struct fmrx_pipeline {
     float *d_pll_state = nullptr;                         // [C][8]
     BufferSet sets[kSets];
     cudaStream_t s_front = nullptr, s_pll = nullptr, s_back = nullptr;
+    cudaStream_t s_h2d = nullptr;   // host path: the H2D copies, so that chunk i+1 comes in under K1/K2 of chunk i
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     long long blocks_done = 0;
     long long chunk_counter = 0;
@@ -346,12 +349,15 @@ void free_pipeline(fmrx_pipeline *p)
         if (s.front_done) cudaEventDestroy(s.front_done);
         if (s.pll_done) cudaEventDestroy(s.pll_done);
         if (s.free_ev) cudaEventDestroy(s.free_ev);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.iq_free) cudaEventDestroy(s.iq_free);
     }
     for (auto &q : p->d_stage) F(q);
     for (auto e : p->tev) cudaEventDestroy(e);
     if (p->ev_in) cudaEventDestroy(p->ev_in);
     if (p->ev_out) cudaEventDestroy(p->ev_out);
     if (p->s_front) cudaStreamDestroy(p->s_front);
+    if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
     if (p->s_pll) cudaStreamDestroy(p->s_pll);
     if (p->s_back) cudaStreamDestroy(p->s_back);
     delete p;
@@ -443,12 +449,15 @@ int create_impl(fmrx_pipeline *p, const fmrx_config *cfg)
         CU(cudaEventCreateWithFlags(&s.front_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.pll_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.free_ev, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.iq_free, cudaEventDisableTiming));
     }
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CU(cudaStreamCreateWithPriority(&p->s_front, cudaStreamNonBlocking, lo));
     CU(cudaStreamCreateWithPriority(&p->s_pll, cudaStreamNonBlocking, hi));   // the long pole first
     CU(cudaStreamCreateWithPriority(&p->s_back, cudaStreamNonBlocking, lo));
+    CU(cudaStreamCreateWithPriority(&p->s_h2d, cudaStreamNonBlocking, lo));
     CU(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
     return reset_state(p);
@@ -561,8 +570,14 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
         if (host_io) {
             iq_dev = S.iq;
             iq_dev_stride = static_cast<size_t>(p->chunk_blocks) * mi.block_size;
+            // on its own stream: the copy of a chunk only waits for the staging buffer (read for the
+            // last time by K1 three chunks ago), not for K1/K2 of the chunk before
+            if (S.iq_free_pending)
+                CU(cudaStreamWaitEvent(p->s_h2d, S.iq_free, 0));
             CU(copy2d(S.iq, iq_dev_stride, iq + b0 * mi.block_size, iq_stride, chunk_bytes, C,
-                      p->s_front, cudaMemcpyHostToDevice));
+                      p->s_h2d, cudaMemcpyHostToDevice));
+            CU(cudaEventRecord(S.h2d_done, p->s_h2d));
+            CU(cudaStreamWaitEvent(p->s_front, S.h2d_done, 0));
         } else {
             iq_dev = iq + b0 * mi.block_size;
             iq_dev_stride = iq_stride;
@@ -597,6 +612,10 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
         CU(copy2d(p->d_hist_iq, 2 * static_cast<size_t>(p->hist_pairs),
                   iq_dev + chunk_bytes - 2 * static_cast<size_t>(p->hist_pairs), iq_dev_stride,
                   2 * static_cast<size_t>(p->hist_pairs), C, p->s_front));
+        if (host_io) {
+            CU(cudaEventRecord(S.iq_free, p->s_front));
+            S.iq_free_pending = true;
+        }
         {
             BandpassArgs a{};
             a.demod = S.demod;
