@@ -1,6 +1,6 @@
 """Quick device-side timing probe (not the benchmark): per-kernel-family times of the
 fused pipeline on synthetic captures resident in HBM."""
-import argparse, importlib, json, sys, time
+import argparse, importlib, json, os, sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -9,6 +9,8 @@ import torch
 
 pkg = importlib.import_module("software-defined-radio-course-project_b200")
 fm = pkg.binding
+if os.environ.get("FMRX_LIB"):           # development: a `make PROFILE=1 LIB=...` build of the library
+    fm.LIB_PATH = Path(os.environ["FMRX_LIB"])
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--captures", type=int, default=64)
@@ -17,13 +19,17 @@ ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--taps", type=int, default=51)
 ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--gpu-synth", action="store_true", help="generate the capture on the GPU (long captures)")
 ap.add_argument("--split", type=float, default=0.0, help="seconds processed in a first call (timed separately)")
 a = ap.parse_args()
 
 info = fm.mode_table(a.mode, a.taps)
 nb = max(1, int(a.seconds * info.rf_fs * 2 / info.block_size))
 C = a.captures
-one = torch.from_numpy(pkg.synth.synth_iq(nb * info.block_size // 2, info.rf_fs, seed=0)).cuda()
+if a.gpu_synth:
+    one = pkg.synth.synth_iq_torch(nb * info.block_size // 2, 1, torch.device("cuda"), info.rf_fs, seed=0)[0]
+else:
+    one = torch.from_numpy(pkg.synth.synth_iq(nb * info.block_size // 2, info.rf_fs, seed=0)).cuda()
 iq = one.unsqueeze(0).repeat(C, 1).contiguous()
 pcm = torch.zeros((C, nb * 2 * info.audio_per_block), dtype=torch.int16, device="cuda")
 p = fm.Pipeline(a.mode, a.taps, C, chunk_blocks=a.chunk)
