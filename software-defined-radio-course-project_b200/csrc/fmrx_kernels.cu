@@ -562,6 +562,7 @@ struct TableRun {
     int cont;                        // the group continues the one before: pi of its first block comes from the predictor too
 #ifdef FMRX_PLL_PROFILE
     int prof_stamp, prof_c, prof_fatal_exact;
+    int prof_tie, prof_range, prof_inv;      // why a block's guard failed: near a rounding tie, grid point not one of the three, no valid table
 #endif
     int gi;                          // in: grid index of the trigArg before the group; out: of the last one
     int n_exact;                     // out: blocks of 16 that had to be stepped the exact way
@@ -766,6 +767,11 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
 #ifdef FMRX_PLL_PROFILE
             r.prof_stamp += bad != 0;
             r.prof_c += bad == 0;
+            if (bad == 0) {
+                if (!(cmax < 1e30f)) r.prof_inv++;
+                else if (cmax > 0.5f) r.prof_range++;
+                else r.prof_tie++;
+            }
 #endif
             r.kbase = kbase;
             r.integ = integ0;            // by value through r: nothing on the chain has its address taken
@@ -986,6 +992,10 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     long long prof_steps_cyc = 0, prof_wait = 0, prof_pre = 0;
     const long long prof_k0 = clock64();
     int prof_steps = 0, prof_n_stamp = 0, prof_n_c = 0, prof_n_fe = 0, prof_n_fm = 0;
+    int prof_n_tie = 0, prof_n_range = 0, prof_n_inv = 0;
+    __shared__ int s_prof[8];        // candidate warps: why a table was not emitted
+    if (threadIdx.x < 8)
+        s_prof[threadIdx.x] = 0;
 #endif
     if (warp == 0) {
         ch.integ = st[0];
@@ -1107,6 +1117,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 r.cont = s_flag[3];
 #ifdef FMRX_PLL_PROFILE
                 r.prof_stamp = r.prof_c = r.prof_fatal_exact = 0;
+                r.prof_tie = r.prof_range = r.prof_inv = 0;
 #endif
                 r.gi = __double2int_rn(p_mul(ch.tad, inv_ulp));                  // exact: trigArg is on the grid
                 r.n_exact = 0;
@@ -1127,6 +1138,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     prof_n_stamp += r.prof_stamp;
                     prof_n_c += r.prof_c;
                     prof_n_fe += r.prof_fatal_exact;
+                    prof_n_tie += r.prof_tie;
+                    prof_n_range += r.prof_range;
+                    prof_n_inv += r.prof_inv;
                     prof_n_fm += r.fatal && !r.prof_fatal_exact;
 #endif
                     good = r.fatal == 0;
@@ -1232,9 +1246,22 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     // the float grid of the binade is only right strictly inside it
                     const int ag = gl < 0 ? -gl : gl;
                     bool ok = have && ag > (1 << 23) && ag < (1 << 24);
+#ifdef FMRX_PLL_PROFILE
+                    const bool prof_ok_b = ok;
+#endif
                     const float ed = error_from_feedback(f, nx.x, nx.xd, ok);         // :159-161 of sample u+1
                     // the table is good if the guards of its three grid points held
                     const int n1 = gc - (vi + kb) - 0x4B400000;                       // G_c - (vi + pi): small
+#ifdef FMRX_PLL_PROFILE
+                    if (live && jq < 3 && blockIdx.x == 0) {
+                        if (!(pr.y == u + 1)) atomicAdd(&s_prof[0], 1);
+                        else if (!have_pi) atomicAdd(&s_prof[1], 1);
+                        else if (!prof_ok_b) atomicAdd(&s_prof[2], 1);
+                        else if (!ok) atomicAdd(&s_prof[fabs(f.phi) >= FMRX_SEAM_PHI_MAX ? 3 : 4], 1);
+                        else if (!(n1 >= -60 && n1 <= 60)) atomicAdd(&s_prof[5], 1);
+                        else atomicAdd(&s_prof[6], 1);
+                    }
+#endif
                     ok = ok && n1 >= -60 && n1 <= 60;
                     const unsigned oks = __ballot_sync(0xffffffffu, ok || jq == 3);
                     const bool valid = ((oks >> (4 * sq)) & 7u) == 7u;
@@ -1343,6 +1370,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         st[3] = fq;
         st[5] = ch.toff;
 #ifdef FMRX_PLL_PROFILE
+        if (c == 0)
+            printf("pll dbg why: blocks near a tie %d, grid point not among the three %d, no valid table %d | candidate lanes: record late %d, no block pi %d, binade edge %d, phi at the seam %d, cross/dot %d, |n1| > 60 %d, ok %d\n",
+                   prof_n_tie, prof_n_range, prof_n_inv, s_prof[0], s_prof[1], s_prof[2], s_prof[3], s_prof[4], s_prof[5], s_prof[6]);
         if (c == 0)
             printf("pll dbg: groups %d exact blocks %d (stamp/pi %d, guard %d) redone %d (exact step left the grid %d, too many exact blocks %d) | %.1f cyc/step over %d table steps | kernel %.1f cyc/step; per group: before wait %.0f, wait for tables %.0f, steps %.0f, rest %.0f\n",
                    n_groups, n_exact, prof_n_stamp, prof_n_c, n_redone, prof_n_fe, prof_n_fm, prof_steps ? (double)prof_steps_cyc / prof_steps : 0.0, prof_steps, (double)(clock64() - prof_k0) / n,

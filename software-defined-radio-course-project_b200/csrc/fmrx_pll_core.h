@@ -88,6 +88,7 @@ FMRX_HD int p_hi32(double a)
 
 // ---- constants ---------------------------------------------------------------
 #define FMRX_FAST_TRIG_MAX 16777216.0f     /* |x| <= 2^24 */
+#define FMRX_SEAM_PHI_MAX 3.1415916        /* pi - 1.05e-6: how close to the +-pi seam the atan2 shortcut goes */
 #define FMRX_RINT_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
 
 // pi/2 = P1 + P2 + P3: 29 + 29 + 53 bits (n*P1, n*P2 exact for |n| < 2^24, which
@@ -181,15 +182,22 @@ FMRX_HD float cos_of_float(float a)
 }
 
 // r + j*pi/2 for the quadrant count m (an integer in a double), with
-// j = m - 4*rint(m/4) in -2..2: the argument wrapped to (-pi, pi].  For m = 2
-// (mod 4) the tie goes to even, so the result may land just outside that interval;
-// this only happens next to the +-pi seam, where the guard sends the step to the
-// generic path anyway.
+// j = m - 4*rint(m/4) in -2..2: the argument wrapped to (-pi, pi].  For m = 2 (mod 4)
+// the tie of the rint goes to even, i.e. to either side: the half turn is then taken with
+// the sign that keeps the result inside the interval (+pi + r for r < 0, -pi + r for
+// r > 0).  Only r == 0 there (trigArg an exact odd multiple of pi: the seam itself) is
+// left to the guard of error_from_feedback.  An unlocked loop visits every quadrant; a
+// locked one stays at m = 0.
 FMRX_HD double wrapped_angle(const TrigK &K, double m, double r)
 {
     const double t = p_add(p_fma(m, 0.25, FMRX_RINT_MAGIC), -FMRX_RINT_MAGIC);
     const double jd = p_fma(-4.0, t, m);        // exact
-    return p_fma(jd, K.pio2_hi, p_fma(jd, K.pio2_lo, r));
+    // both signs of the half turn are evaluated beside each other and one select follows r (this
+    // is on the dependent chain of the exact step); same sign bit of j and r = the wrong side
+    const double same = p_fma(jd, K.pio2_hi, p_fma(jd, K.pio2_lo, r));
+    const double other = p_fma(-jd, K.pio2_hi, p_fma(-jd, K.pio2_lo, r));
+    const bool flip = fabs(jd) == 2.0 && (p_hi32(jd) ^ p_hi32(r)) >= 0;
+    return flip ? other : same;
 }
 
 struct Consts {
@@ -365,7 +373,9 @@ FMRX_HD float error_from_feedback(const Feedback &f, float x, double xd, bool &o
     const double dotc = p_fma(-f.snx, tq, p_mul(f.csx, ti));   // radial part (second order)
     const double a1 = p_fma(-f.snx, ti, p_add(f.phi, -m1));    // phi + cross
     const double alpha = p_fma(-cross, dotc, a1);              // phi + cross*(1 - dotc)
-    ok = ok && fabs(cross) < 0x1p-20 && fabs(dotc) < 0x1p-20 && fabs(f.phi) < 3.125;
+    // the result must not wrap at the +-pi seam: |alpha| <= |phi| + |cross| (1 + |dotc|) < pi
+    // with |cross| < 2^-20 = 9.54e-7 and |phi| < pi - 1.05e-6
+    ok = ok && fabs(cross) < 0x1p-20 && fabs(dotc) < 0x1p-20 && fabs(f.phi) < FMRX_SEAM_PHI_MAX;
     return p_d2f(-alpha);                                            // :161
 }
 
