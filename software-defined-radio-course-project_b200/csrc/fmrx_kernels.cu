@@ -1022,8 +1022,13 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         // ---- group header (warp 0) ----
         if (warp == 0) {
             ck = ch;
+            // The hypotheses of a step are NEIGHBOURING float-grid points of trigArg, which presumes that
+            // phaseEst moves on a grid at least as fine.  Where the reference hands the PLL if_fs*interp
+            // (modes 2/3) phaseEst cancels w*trigOffset, trigArg is a small difference of large floats and
+            // its possible values lie a whole phaseEst spacing (thousands of its own grid steps) apart:
+            // no tables there.
             const bool spec = regular && !dead && skip == 0 && ch.binade != FMRX_DISARMED &&
-                              s_prep_ulp[g & 3] == ch.ulp;
+                              s_prep_ulp[g & 3] == ch.ulp && (double)fabsf(ch.ph) < ch.ulp * 16777216.0;
             if (lane == 0) {
                 s_flag[0] = spec;
                 s_grid[0] = ch.ulp;
