@@ -93,6 +93,28 @@ def test_pll_float_counter_saturates(fm, port):
     assert_bits_equal(gs, os_, "pll state at saturation")
 
 
+@pytest.mark.parametrize("fs", [240e3, 288e3])
+def test_pll_long_run_past_counter_saturation(fm, port, fs):
+    """Past 2^24 samples trigArg freezes on two neighbouring float grid points 0.5 rad apart and the
+    loop stops tracking: the phase detector's angle is then anywhere on the circle, not near 0 as on a
+    locked loop (mode 0 reaches this after 69.9 s, mode 1 -- 288 kHz -- after 58.3 s).  k_pll's
+    candidate tables must serve that regime too; bit-identical over 150 groups of it."""
+    n = 160000
+    t = np.arange(n, dtype=np.float64)
+    rng = np.random.default_rng(9)
+    pilot = (0.1 * np.sin(2 * np.pi * 19000 / fs * t) + 0.002 * rng.standard_normal(n)).astype(np.float32)
+    # lock first, then move the counter next to its limit with a feedback pair that belongs to the state
+    _, _, st = port.pll(pilot[:60000], 19000, fs, 2, 0, 0.01)
+    st[5] = 16777216.0 - 4000.0
+    ta = np.float32(2 * np.pi * np.float64(np.float32(19000) / np.float32(fs)) * np.float64(st[5]) + np.float64(st[1]))
+    st[2], st[3] = np.float32(np.cos(np.float64(ta))), np.float32(np.sin(np.float64(ta)))
+    g, gs = fm.PLL(pilot[60000:], 19000, fs, 2, 0, 0.01, st)
+    o, _, os_ = port.pll(pilot[60000:], 19000, fs, 2, 0, 0.01, st)
+    assert gs[5] == 16777216.0
+    assert_bits_equal(g, o, "pll nco past saturation")
+    assert_bits_equal(gs, os_, "pll state past saturation")
+
+
 def test_pll_other_parameters(fm, port):
     """The (dead) RDS path calls PLL(114000, bp_fs, 0.5, 0, 0.01) (src/project.cpp:250)."""
     t = np.arange(30000, dtype=np.float64)

@@ -136,3 +136,29 @@ def test_fast_pll_bitwise_on_hostile_inputs(model, port, kind):
     _, otrig, ost = port.pll(x, 19000, 240e3, 2, 0, 0.01)
     assert_bits_equal(trig, otrig, f"trigArg ({kind})")
     assert_bits_equal(st[:2], ost[:2], f"integrator, phaseEst ({kind})")
+
+
+@pytest.mark.parametrize("kind,fs,toff0", [("noise", 240e3, 0.0), ("offtune", 288e3, 0.0), ("saturated", 288e3, 16777216.0 - 3000.0)])
+def test_fast_step_covers_every_quadrant_of_an_unlocked_loop(model, port, kind, fs, toff0):
+    """On a locked loop the phase detector's wrapped angle stays near 0; a loop that does not lock
+    (no pilot, pilot off tune, trigOffset saturated at 2^24) takes it through all four quadrants.
+    The atan2 shortcut must serve all of them (wrapped_angle: the half turn on the side that stays
+    inside (-pi, pi]) and leave only the +-pi seam itself to the exact fall-back: bit-identical to
+    the oracle with well under 0.1 % of the steps on the generic path (it was 0.7 % when half of the
+    second quadrant went to the guard, enough to invalidate every candidate table of k_pll)."""
+    n = 600000
+    rng = np.random.default_rng(21)
+    if kind == "noise":
+        x = rng.uniform(-1, 1, n).astype(np.float32)
+    else:
+        f = 17000.0 if kind == "offtune" else 19000.0
+        x = (0.1 * np.sin(2 * np.pi * f / fs * np.arange(n)) + 0.01 * rng.standard_normal(n)).astype(np.float32)
+    fi, fq = C.c_float(1.0), C.c_float(0.0)
+    if toff0:
+        model.pll_model_feedback.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, f32p, f32p]
+        model.pll_model_feedback(19000.0, fs, 0.0, toff0, C.byref(fi), C.byref(fq))
+    trig, st, slow = run_model(model, x, 19000.0, fs, [0, 0, fi.value, fq.value, toff0])
+    _, otrig, ost = port.pll(x, 19000, fs, 2, 0, 0.01, [0, 0, fi.value, fq.value, 0, toff0])
+    assert_bits_equal(trig, otrig, f"trigArg ({kind})")
+    assert_bits_equal(st[:2], ost[:2], f"integrator, phaseEst ({kind})")
+    assert slow < 1e-3 * n, f"{slow} of {n} steps left the fast path"
