@@ -1034,15 +1034,30 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             // out different from the reference in 1.4 % of its trigArgs -- tests/test_gpu_operators.py::
             // test_pll_long_run_past_counter_saturation -- and until that is understood the regime takes the
             // exact step, which the host build of the same code verifies bit for bit there)
+            // the group before ran on tables to its end and hardly needed the exact step: predictor and
+            // candidates did our head, and the predictor carries on from its own state (otherwise it
+            // restarts from the exact one: it may have drifted)
+            const bool cont = spec && have_ed && prev_exact <= 2;
+            if (!cont && base > 0) {
+                // ... and then the head that the group before prepared must go: its tables carry this
+                // group's stamps and its records this group's sequence numbers, but their block pi came
+                // from the OLD predictor run, while warp 0 now takes pi of the first block from the exact
+                // phaseEst -- where the two differ (phaseEst/ulp near a half-integer: a loop sitting on a
+                // rounding boundary, e.g. past counter saturation) the thresholds select a neighbouring
+                // hypothesis without any guard noticing (reproduced on the host: tests/pll_model.cpp,
+                // pll_model_stale_head).  Everyone is behind the barrier that ended the last group.
+                for (int i = lane; i < PLL_HEAD; i += 32) {
+                    s_tab[(base + i) & (PLL_TABLES - 1)].lp = PLL_ROW_INVALID;
+                    s_tab[(base + i) & (PLL_TABLES - 1)].stamp = 0;
+                    s_ph[(base + i) & (PLL_PH_RING - 1)] = make_int2(0, 0);
+                }
+            }
             if (lane == 0) {
                 s_flag[0] = spec;
                 s_grid[0] = ch.ulp;
                 s_grid[1] = ch.inv_ulp;
                 s_flag[2] = s_prep_ulp[(g + 1) & 3] != ch.ulp;
-                // the group before ran on tables to its end and hardly needed the exact step: predictor and
-                // candidates did our head, and the predictor carries on from its own state (otherwise it
-                // restarts from the exact one: it may have drifted)
-                s_flag[3] = spec && have_ed && prev_exact <= 2;
+                s_flag[3] = cont;
                 s_kbase = __float_as_int(p_faddf(p_fmulf(ch.ph, (float)ch.inv_ulp), 12582912.0f)) - 0x4B400000 - 0x4B400000;
                 s_hdr[0] = ch.integ;
                 s_hdr[1] = ch.ph;

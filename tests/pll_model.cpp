@@ -144,3 +144,221 @@ extern "C" void pll_model_feedback(float freq, float Fs, float ph, float toff, f
         *fq = (float)sin(c.tad);
     }
 }
+
+// ---- the candidate-table path of k_pll, sequentially ----------------------------------------
+//
+// Same arithmetic as the kernel's three kinds of warp (csrc/fmrx_kernels.cu: prepare(), the
+// predictor, the candidate tables, pll_table_group, pll_block_exact), without the concurrency:
+// groups of 1024 steps, the predictor restarted from the exact state at every group, pi per
+// block of 16 from the predictor's phaseEst of the step before it, three hypotheses per step
+// selected by comparing t = fma(phaseEst, 1/ulp, -pi) with the table's thresholds, the same
+// guards, a block with a failed guard stepped again the exact way.  Lets a regime that the
+// tables get wrong be found on the CPU.  stats: [0] table blocks, [1] exact blocks, [2] groups
+// without tables.
+// pll_model_stale_head = 1 reproduces a hazard k_pll had: the predictor and the candidate warps do the
+// first 48 steps of the NEXT group at the end of a group; if that next group then does not continue its
+// predecessor (it restarts from the exact state because the predecessor needed exact blocks), those
+// tables -- centred and, worse, given their block pi by the OLD predictor run -- still carried valid
+// stamps and were used with the pi warp 0 takes from the exact phaseEst.
+extern "C" {
+int pll_model_stale_head = 0;
+}
+
+extern "C" int pll_model_tables(const float *pilot, int n, float freq, float Fs, float bw, float *state5,
+                                float *trig_out, long long *stats)
+{
+    Consts k;
+    k.kp = bw * 2.666f;
+    k.ki = (bw * bw) * 3.555f;
+    k.w = (2.0 * 3.14159265358979323846) * (double)(freq / Fs);
+    const TrigK K = trig_constants();
+    Chain c;
+    memset(&c, 0, sizeof(c));
+    c.integ = state5[0]; c.ph = state5[1]; c.fi = state5[2]; c.fq = state5[3]; c.toff = state5[4];
+    chain_load(c, k);
+    const int GROUP = 1024;
+    struct In { float x; double xd, inv_x, turn, v; int vi; float vr, cpred; };
+    static In in[GROUP + 1];
+    static float php[GROUP];            // the predictor's phaseEst after each step
+    static float php_stale[48];         // ... of the first 48 steps, by the run that continued from the group before
+    float stale_integ = 0.0f, stale_ph = 0.0f, stale_prev = 0.0f;
+    bool have_stale = false;
+    auto bits = [](float f) { int i; memcpy(&i, &f, 4); return i; };
+    auto fbits = [](int i) { float f; memcpy(&f, &i, 4); return f; };
+    for (int base = 0; base < n; base += GROUP) {
+        const int cnt = n - base < GROUP ? n - base : GROUP;
+        bool spec = toff_is_regular(c.toff) && c.binade != FMRX_DISARMED && cnt == GROUP && base + GROUP < n;
+        const double ulp = c.ulp, inv_ulp = c.inv_ulp;
+        const float inv_ulp_f = (float)inv_ulp;
+        const Chain ck = c;
+        bool good = spec;
+        if (spec) {
+            // prepare(): per-sample inputs of this group (and the first of the next: the last table needs it)
+            for (int j = 0; j <= GROUP; j++) {
+                const int u = base + j;
+                In &i = in[j];
+                i.x = pilot[u];
+                i.xd = (double)i.x;
+                i.inv_x = 1.0 / i.xd;
+                i.turn = i.x < 0.0f ? 2.0 : 0.0;
+                const float toff = toff_after(ck.toff, j + 1);
+                i.v = p_mul(k.w, (double)toff);
+                const double qv = grid_round(i.v, inv_ulp);
+                i.vi = grid_index(qv);
+                i.vr = (float)p_fma(i.v, inv_ulp, -p_add(qv, -FMRX_RINT_MAGIC));
+                i.cpred = predictor_c(k, i.x, toff_after(ck.toff, j));
+            }
+            // the predictor, from the exact state
+            {
+                if (have_stale) {
+                    float pi = stale_integ, pp = stale_ph;
+                    for (int j = 0; j < 48; j++) {
+                        predictor_step(k, in[j].cpred, pi, pp);
+                        php_stale[j] = pp;
+                    }
+                }
+                float pi = ck.integ, pp = ck.ph;
+                for (int j = 0; j < GROUP; j++) {
+                    predictor_step(k, in[j].cpred, pi, pp);
+                    php[j] = pp;
+                }
+                stale_integ = pi;
+                stale_ph = pp;
+            }
+            const bool use_stale = pll_model_stale_head && have_stale;
+            const float stale_prev_now = stale_prev;
+            long long exact_before = stats[1];
+            float integ = c.integ, ph = c.ph;
+            // Kp*errorD, Ki*errorD of the first sample, from the known trigArg
+            float kpe, kie;
+            {
+                const Feedback f0 = make_feedback(K, c.tad, in[0].turn, in[0].inv_x, nullptr, nullptr);
+                const float ed = error_from_feedback(f0, in[0].x, in[0].xd, good);
+                kpe = k.kp * ed;
+                kie = k.ki * ed;
+            }
+            int gi = grid_index(grid_round(c.tad, inv_ulp));
+            for (int t = 0; good && t < GROUP; t += 16) {
+                // pi of the block
+                const float ph_for_pi = t == 0 ? ph : php[t - 1];
+                const float pm = ph_for_pi * inv_ulp_f + 12582912.0f;
+                const float pi_f = pm - 12582912.0f;
+                const int pi_i = bits(pm) - 0x4B400000;
+                if (!(fabsf(pi_f) < 2097152.0f)) { good = false; break; }
+                const float integ0 = integ, ph0 = ph;
+                const int gi0 = gi;
+                integ = integ + kie;
+                ph = ph + (kpe + integ);
+                bool bad = false;
+                float cmax = 0.0f;
+                int gidx[16];
+                for (int j = 0; j < 16; j++) {
+                    const int u = t + j;
+                    // the candidate table of step u: hypotheses G_c - 1, G_c, G_c + 1 of trigArg(u) -> errorD of sample u + 1
+                    const bool st = use_stale && u < 48;
+                    const int gc = grid_index(grid_round(p_add(in[u].v, (double)(st ? php_stale[u] : php[u])), inv_ulp));
+                    int pi_tab = pi_i;          // the pi the candidate warps used for this block
+                    if (st) {
+                        const float phs = t == 0 ? stale_prev_now : php_stale[t - 1];
+                        pi_tab = bits(phs * inv_ulp_f + 12582912.0f) - 0x4B400000;
+                    }
+                    float kpe_h[3], kie_h[3];
+                    bool ok = true;
+                    for (int h = 0; h < 3; h++) {
+                        const int gl = gc - 1 + h;
+                        const double tad = p_mul((double)gl, ulp);
+                        const Feedback f = make_feedback(K, tad, in[u + 1].turn, in[u + 1].inv_x, nullptr, nullptr);
+                        const int ag = gl < 0 ? -gl : gl;
+                        bool okh = ag > (1 << 23) && ag < (1 << 24);
+                        const float ed = error_from_feedback(f, in[u + 1].x, in[u + 1].xd, okh);
+                        kpe_h[h] = k.kp * ed;
+                        kie_h[h] = k.ki * ed;
+                        ok = ok && okh;
+                    }
+                    const int n1 = gc - (in[u].vi + pi_tab);
+                    ok = ok && n1 >= -60 && n1 <= 60;
+                    const float lp = ok ? ((float)n1 + -0.5f) + -in[u].vr : 0x1p100f;
+                    // the chain step
+                    const float hp = lp + 1.0f, lc = lp + 0.5f;
+                    const float tt = fmaf(ph, inv_ulp_f, -pi_f);
+                    const int sel = tt < lp ? 0 : tt > hp ? 2 : 1;
+                    if (j < 15) {
+                        const float i_s = integ + kie_h[sel];
+                        const float p_s = ph + (kpe_h[sel] + i_s);
+                        integ = i_s;
+                        ph = p_s;
+                    } else {
+                        kpe = kpe_h[sel];
+                        kie = kie_h[sel];
+                    }
+                    const float q = tt + -lc;
+                    cmax = fmaxf(cmax, fabsf(fabsf(fabsf(q) + -0.5f) + -0.5f));
+                    gidx[j] = in[u].vi + pi_i + (bits((tt + in[u].vr) + 12582912.0f) - 0x4B400000);
+                }
+                if (bad || !(cmax < 0.5f - 0x1p-15f)) {
+                    // the block again, the exact way (pll_block_exact)
+                    stats[1]++;
+                    Chain e;
+                    memset(&e, 0, sizeof(e));
+                    e.integ = integ0;
+                    e.ph = ph0;
+                    e.toff = toff_after(ck.toff, t);
+                    e.tad = p_mul((double)gi0, ulp);
+                    chain_refresh(e);
+                    for (int j = 0; j < 16; j++) {
+                        if (e.binade == FMRX_DISARMED || e.ulp != ulp) { good = false; break; }
+                        const In &i = in[t + j];
+                        StepIn si;
+                        si.x = i.x; si.xd = i.xd; si.inv_x = i.inv_x; si.turn = i.turn; si.v = i.v;
+                        if (!chain_step_fast(e, k, K, si))
+                            chain_step_generic(e, k, i.x);
+                        gidx[j] = grid_index(grid_round(e.tad, e.inv_ulp));
+                    }
+                    if (!good || e.binade == FMRX_DISARMED || e.ulp != ulp) { good = false; break; }
+                    const In &nx = in[t + 16];
+                    const Feedback f = make_feedback(K, e.tad, nx.turn, nx.inv_x, nullptr, nullptr);
+                    bool ok = true;
+                    float ed = error_from_feedback(f, nx.x, nx.xd, ok);
+                    if (!ok) {
+                        float fi, fq;
+                        chain_feedback(e, fi, fq);
+                        ed = (float)atan2((double)(nx.x * -fq), (double)(nx.x * fi));
+                    }
+                    kpe = k.kp * ed;
+                    kie = k.ki * ed;
+                    integ = e.integ;
+                    ph = e.ph;
+                } else {
+                    stats[0]++;
+                }
+                gi = gidx[15];
+                for (int j = 0; j < 16; j++)
+                    trig_out[base + t + j] = (float)p_mul((double)gidx[j], ulp);
+            }
+            have_stale = good && stats[1] - exact_before > 2;      // the next group will not "continue" this one
+            stale_prev = php[GROUP - 1];
+            if (good) {
+                // (integ, ph) are the state after sample base + GROUP - 1 with the next sample's errorD pending:
+                // rebuild the chain from the last trigArg
+                c.integ = integ;
+                c.ph = ph;
+                c.toff = toff_after(ck.toff, GROUP);
+                c.tad = p_mul((double)gi, ulp);
+                chain_refresh(c);
+                if (c.ulp != ulp)
+                    ;                     // binade change: the next group starts on the new grid
+            }
+        }
+        if (!good) {
+            have_stale = false;
+            stats[2]++;
+            c = ck;
+            for (int t = 0; t < cnt; t++)
+                trig_out[base + t] = chain_step(c, k, K, pilot[base + t], nullptr);
+        }
+    }
+    state5[0] = c.integ; state5[1] = c.ph; state5[4] = c.toff;
+    chain_feedback(c, state5[2], state5[3]);
+    (void)fbits;
+    return 0;
+}

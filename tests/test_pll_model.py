@@ -162,3 +162,63 @@ def test_fast_step_covers_every_quadrant_of_an_unlocked_loop(model, port, kind, 
     assert_bits_equal(trig, otrig, f"trigArg ({kind})")
     assert_bits_equal(st[:2], ost[:2], f"integrator, phaseEst ({kind})")
     assert slow < 1e-3 * n, f"{slow} of {n} steps left the fast path"
+
+
+def run_tables(L, x, fs, st6, stale_head=False):
+    L.pll_model_tables.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, f32p, f32p, C.POINTER(C.c_longlong)]
+    C.c_int.in_dll(L, "pll_model_stale_head").value = int(stale_head)
+    st = np.array([st6[0], st6[1], st6[2], st6[3], st6[5]], np.float32)
+    trig = np.zeros(len(x), np.float32)
+    stats = np.zeros(4, np.int64)
+    L.pll_model_tables(x.ctypes.data_as(f32p), len(x), 19000.0, fs, 0.01, st.ctypes.data_as(f32p),
+                       trig.ctypes.data_as(f32p), stats.ctypes.data_as(C.POINTER(C.c_longlong)))
+    C.c_int.in_dll(L, "pll_model_stale_head").value = 0
+    return trig, st, stats
+
+
+def saturating_case(port, fs):
+    """The input of tests/test_gpu_operators.py::test_pll_long_run_past_counter_saturation."""
+    n = 160000
+    t = np.arange(n, dtype=np.float64)
+    rng = np.random.default_rng(9)
+    pilot = (0.1 * np.sin(2 * np.pi * 19000 / fs * t) + 0.002 * rng.standard_normal(n)).astype(np.float32)
+    _, _, st = port.pll(pilot[:60000], 19000, fs, 2, 0, 0.01)
+    st[5] = 16777216.0 - 4000.0
+    ta = np.float32(2 * np.pi * np.float64(np.float32(19000) / np.float32(fs)) * np.float64(st[5]) + np.float64(st[1]))
+    st[2], st[3] = np.float32(np.cos(np.float64(ta))), np.float32(np.sin(np.float64(ta)))
+    return pilot[60000:], st
+
+
+@pytest.mark.parametrize("case", ["locked_240k", "locked_288k", "saturating_240k", "saturating_288k", "noise"])
+def test_candidate_table_arithmetic_bitwise(model, port, case):
+    """k_pll's table path, sequentially on the host (tests/pll_model.cpp, pll_model_tables: predictor,
+    three hypotheses per step, threshold selection, guards, exact blocks): bit-identical to the oracle on a
+    locked loop, across the counter's saturation (where trigArg toggles between two grid points and the
+    loop sits on a float rounding boundary) and on noise; most blocks must really run on tables."""
+    fs = 288e3 if "288k" in case else 240e3
+    if case.startswith("saturating"):
+        x, st = saturating_case(port, fs)
+    else:
+        n = 200000
+        rng = np.random.default_rng(31)
+        x = (rng.uniform(-1, 1, n) if case == "noise"
+             else 0.1 * np.sin(2 * np.pi * 19000.4 / fs * np.arange(n) + 0.3) + 0.003 * rng.standard_normal(n)).astype(np.float32)
+        st = np.array([0, 0, 1, 0, 0, 0], np.float32)
+    trig, s5, stats = run_tables(model, x, fs, st)
+    _, otrig, ost = port.pll(x, 19000, fs, 2, 0, 0.01, st)
+    assert_bits_equal(trig, otrig, f"trigArg ({case})")
+    assert_bits_equal(s5[:2], ost[:2], f"integrator, phaseEst ({case})")
+    if case != "noise":
+        assert stats[0] > 4 * stats[1], stats          # (the first 0.1 s of a capture, on its fine float grids, needs many exact blocks)
+
+
+def test_stale_head_tables_would_diverge(model, port):
+    """The hazard behind the one GPU parity failure of round 1: a group that does not continue its
+    predecessor must not use the head tables the predecessor prepared for it (their block pi came from the
+    old predictor run).  With the hazard switched on, the host model leaves the reference at the very sample
+    the GPU did (288 kHz, step 4098 of the saturating case); k_pll now invalidates such a head."""
+    x, st = saturating_case(port, 288e3)
+    _, otrig, _ = port.pll(x, 19000, 288e3, 2, 0, 0.01, st)
+    trig, _, _ = run_tables(model, x, 288e3, st, stale_head=True)
+    ne = np.nonzero(trig.view(np.uint32) != otrig.view(np.uint32))[0]
+    assert len(ne) and ne[0] == 4098
