@@ -1032,8 +1032,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                               t0 + base + cnt < 16777216;
             // (no tables once trigOffset sits at 2^24 either: a 288 kHz loop run on tables past that point came
             // out different from the reference in 1.4 % of its trigArgs -- tests/test_gpu_operators.py::
-            // test_pll_long_run_past_counter_saturation -- and until that is understood the regime takes the
-            // exact step, which the host build of the same code verifies bit for bit there)
+            // test_pll_long_run_past_counter_saturation.  The cause is the stale head dealt with just below;
+            // the restriction stays until that fix has been run on a GPU: DESIGN.md section 6 and 9.)
+
             // the group before ran on tables to its end and hardly needed the exact step: predictor and
             // candidates did our head, and the predictor carries on from its own state (otherwise it
             // restarts from the exact one: it may have drifted)
