@@ -362,3 +362,55 @@ extern "C" int pll_model_tables(const float *pilot, int n, float freq, float Fs,
     (void)fbits;
     return 0;
 }
+
+// ---- a predictor in the reference's own operation order (design study for modes 2/3) ---------
+//
+// Where phaseEst's float spacing exceeds trigArg's (the reference hands its PLL if_fs*interp in
+// modes 2/3, phaseEst cancels w*trigOffset) the hypotheses of a step have to be neighbouring floats
+// of PHASEEST.  That needs a predictor that follows phaseEst to the bit most of the time: the loop
+// filter exactly as the reference orders it (:163-164), errorD from the ROUNDED trigArg by the
+// identity atan2(x*(-sin t), x*cos t) = wrap(pi*(x < 0) - t) evaluated in double and rounded to
+// float once (right to an ulp or so of the reference's float errorD).  Restarted from the exact state
+// every `group` steps; hist[d + 8] counts steps whose predicted phaseEst is d float spacings from
+// the exact one (clamped to +-8).
+extern "C" int pll_model_predict_exact_order(const float *pilot, int n, float freq, float Fs, float bw, float *state5,
+                                             int group, long long *hist)
+{
+    Consts k;
+    k.kp = bw * 2.666f;
+    k.ki = (bw * bw) * 3.555f;
+    k.w = (2.0 * 3.14159265358979323846) * (double)(freq / Fs);
+    const TrigK K = trig_constants();
+    Chain c;
+    memset(&c, 0, sizeof(c));
+    c.integ = state5[0]; c.ph = state5[1]; c.fi = state5[2]; c.fq = state5[3]; c.toff = state5[4];
+    chain_load(c, k);
+    const double two_pi = 6.283185307179586476925287, pi = 3.14159265358979323846;
+    float pi_ = 0, pp = 0;
+    double pt = 0;                      // the predictor's (rounded) trigArg
+    for (int u = 0; u < n; u++) {
+        if (u % group == 0) {
+            pi_ = c.integ;
+            pp = c.ph;
+            pt = c.tad;
+        }
+        const float x = pilot[u];
+        // errorD of this sample from the predictor's previous trigArg
+        double a = (x < 0.0f ? pi : 0.0) - pt;
+        a -= two_pi * nearbyint(a / two_pi);
+        const float e = (float)a;
+        pi_ = pi_ + k.ki * e;                                  // :163
+        pp = pp + (k.kp * e + pi_);                            // :164
+        const float toff = toff_after(c.toff, 1);
+        pt = (double)(float)(k.w * (double)toff + (double)pp); // :166-167
+        chain_step(c, k, K, x, nullptr);
+        const float sp = fabsf(c.ph) > 0 ? nextafterf(fabsf(c.ph), INFINITY) - fabsf(c.ph) : 1e-45f;
+        double d = ((double)pp - (double)c.ph) / (double)sp;
+        int b = (int)nearbyint(d);
+        b = b < -8 ? -8 : b > 8 ? 8 : b;
+        hist[b + 8]++;
+    }
+    state5[0] = c.integ; state5[1] = c.ph; state5[4] = c.toff;
+    chain_feedback(c, state5[2], state5[3]);
+    return 0;
+}
