@@ -414,3 +414,82 @@ extern "C" int pll_model_predict_exact_order(const float *pilot, int n, float fr
     chain_feedback(c, state5[2], state5[3]);
     return 0;
 }
+
+// The one-hypothesis scheme of DESIGN.md section 9 (modes 2/3), sequentially: the exact-order predictor
+// runs a group ahead from the exact state; the exact phase detector is evaluated for the trigArg that
+// follows from the PREDICTED phaseEst of the step before; the exact loop filter runs on those errorDs and a
+// block of 16 is accepted iff its phaseEst matched the predictor's bit for bit at every step (otherwise it
+// is stepped again the exact way).  stats: [0] accepted blocks, [1] exact blocks.
+extern "C" int pll_model_one_hypothesis(const float *pilot, int n, float freq, float Fs, float bw, float *state5,
+                                        float *trig_out, long long *stats)
+{
+    Consts k;
+    k.kp = bw * 2.666f;
+    k.ki = (bw * bw) * 3.555f;
+    k.w = (2.0 * 3.14159265358979323846) * (double)(freq / Fs);
+    const TrigK K = trig_constants();
+    Chain c;
+    memset(&c, 0, sizeof(c));
+    c.integ = state5[0]; c.ph = state5[1]; c.fi = state5[2]; c.fq = state5[3]; c.toff = state5[4];
+    chain_load(c, k);
+    const double two_pi = 6.283185307179586476925287, pi = 3.14159265358979323846;
+    const int GROUP = 1024;
+    static float pph[GROUP];
+    static double pt[GROUP];
+    auto bits = [](float f) { int i; memcpy(&i, &f, 4); return i; };
+    for (int base = 0; base < n; base += GROUP) {
+        const int cnt = n - base < GROUP ? n - base : GROUP;
+        // the predictor, from the exact state
+        {
+            float pi_ = c.integ, pp = c.ph;
+            double t = c.tad;
+            for (int j = 0; j < cnt; j++) {
+                const float x = pilot[base + j];
+                double a = (x < 0.0f ? pi : 0.0) - t;
+                a -= two_pi * nearbyint(a / two_pi);
+                const float e = (float)a;
+                pi_ = pi_ + k.ki * e;
+                pp = pp + (k.kp * e + pi_);
+                t = (double)(float)(k.w * (double)toff_after(c.toff, j + 1) + (double)pp);
+                pph[j] = pp;
+                pt[j] = t;
+            }
+        }
+        for (int tb = 0; tb < cnt; tb += 16) {
+            const int nb = cnt - tb < 16 ? cnt - tb : 16;
+            const Chain ck = c;
+            float integ = c.integ, ph = c.ph;
+            int bad = toff_is_regular(c.toff) ? 0 : 1;
+            for (int j = 0; j < nb && !bad; j++) {
+                const int u = tb + j;
+                const float x = pilot[base + u];
+                const double tprev = u == 0 ? ck.tad : (j == 0 ? c.tad : pt[u - 1]);
+                bool ok = fabs(tprev) <= FMRX_FAST_TRIG_MAX;
+                const Feedback f = make_feedback(K, tprev, x < 0.0f ? 2.0 : 0.0, 1.0 / (double)x, nullptr, nullptr);
+                const float ed = error_from_feedback(f, x, (double)x, ok);
+                integ = integ + k.ki * ed;
+                ph = ph + (k.kp * ed + integ);
+                bad |= !ok;
+                bad |= bits(ph) ^ bits(pph[u]);
+            }
+            if (!bad) {
+                stats[0]++;
+                c.integ = integ;
+                c.ph = ph;
+                c.toff = toff_after(ck.toff, nb);
+                c.tad = pt[tb + nb - 1];
+                chain_refresh(c);
+                for (int j = 0; j < nb; j++)
+                    trig_out[base + tb + j] = (float)pt[tb + j];
+            } else {
+                stats[1]++;
+                c = ck;
+                for (int j = 0; j < nb; j++)
+                    trig_out[base + tb + j] = chain_step(c, k, K, pilot[base + tb + j], nullptr);
+            }
+        }
+    }
+    state5[0] = c.integ; state5[1] = c.ph; state5[4] = c.toff;
+    chain_feedback(c, state5[2], state5[3]);
+    return 0;
+}

@@ -241,3 +241,27 @@ def test_exact_order_predictor_follows_phaseest_in_modes_2_3(model, fs_pll, fs_s
     model.pll_model_predict_exact_order(x.ctypes.data_as(f32p), n, 19000.0, fs_pll, 0.01, st.ctypes.data_as(f32p), 1024,
                                         hist.ctypes.data_as(C.POINTER(C.c_longlong)))
     assert hist[8] > 0.9999 * n, hist.tolist()
+
+
+@pytest.mark.parametrize("case,fs_pll,fs_sig,max_exact", [("mode2", 240e3 * 147, 240e3, 1e-3), ("mode3", 256e3 * 441, 256e3, 1e-3),
+                                                          ("noise", 240e3, 240e3, 1e-2), ("locked", 240e3, 240e3, 1.0)])
+def test_one_hypothesis_scheme_is_exact(model, port, case, fs_pll, fs_sig, max_exact):
+    """The next K3 step, end to end on the host (tests/pll_model.cpp, pll_model_one_hypothesis): predictor in
+    the reference's operation order, exact phase detector for the predicted trigArg, exact loop filter, a block
+    accepted iff phaseEst matched the predictor's bits at every step.  trigArg, integrator and phaseEst come
+    out bit-identical to the oracle in every regime; in modes 2/3 and on an unlocked loop -- where today's
+    three-hypothesis tables cannot work -- almost every block is accepted."""
+    n = 600000
+    rng = np.random.default_rng(1)
+    x = (rng.uniform(-1, 1, n) if case == "noise"
+         else 0.1 * np.sin(2 * np.pi * 19000 / fs_sig * np.arange(n)) + 0.004 * rng.standard_normal(n)).astype(np.float32)
+    model.pll_model_one_hypothesis.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, f32p, f32p, C.POINTER(C.c_longlong)]
+    st = np.array([0, 0, 1, 0, 0], np.float32)
+    stats = np.zeros(4, np.int64)
+    trig = np.zeros(n, np.float32)
+    model.pll_model_one_hypothesis(x.ctypes.data_as(f32p), n, 19000.0, fs_pll, 0.01, st.ctypes.data_as(f32p),
+                                   trig.ctypes.data_as(f32p), stats.ctypes.data_as(C.POINTER(C.c_longlong)))
+    _, otrig, ost = port.pll(x, 19000, fs_pll, 2, 0, 0.01)
+    assert_bits_equal(trig, otrig, f"trigArg ({case})")
+    assert_bits_equal(st[:2], ost[:2], f"integrator, phaseEst ({case})")
+    assert stats[1] <= max_exact * (stats[0] + stats[1]), stats.tolist()
