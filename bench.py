@@ -43,6 +43,9 @@ METRIC = "input IQ Msamples/s (mode 0 stereo)"
 UNIT = "Msamples/s"
 MODE, TAPS = 0, 51
 RF_FS = 2.4e6
+# warp-instructions the chain warp of k_pll issues per step in its steady-state loop (counted in the SASS of
+# pll_table_group: profiles/r02_k_pll_chain_sass.txt)
+PLL_CHAIN_INSTR_PER_STEP = 20
 
 
 def parse_args():
@@ -56,6 +59,10 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="signal per process for the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the whole-run parity check against the oracle")
+    ap.add_argument("--parity-budget", type=float, default=150.0, help="seconds of wall time for the live oracle")
+    ap.add_argument("--no-extras", action="store_true", help="skip the mixed / worst-case legs (N=1 only)")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --captures is the TOTAL, split over the ranks")
     return ap.parse_args()
 
 
@@ -118,7 +125,7 @@ def cpu_sample_input(seconds: float) -> bytes:
     pkg = importlib.import_module("software-defined-radio-course-project_b200")
     info_block = 12800
     n_blocks = max(8, int(seconds * RF_FS * 2 / info_block))
-    return pkg.synth.synth_iq(n_blocks * info_block // 2, RF_FS, seed=0).tobytes()
+    return pkg.synth.synth_iq_exact(n_blocks * info_block // 2, RF_FS, station=0).tobytes()
 
 
 def main_reference(args):
@@ -210,6 +217,93 @@ class ClockSampler:
 # this repo's arm
 # ----------------------------------------------------------------------------------------
 
+def pin_to_gpu_numa(local: int):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the CPU cores nvidia-smi
+    reports as local to GPU `local`.  Returns the affinity string or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        lines = [ln for ln in out.splitlines() if ln.strip()]
+        hdr = next(ln for ln in lines if "CPU Affinity" in ln)
+        cols = [c.strip() for c in hdr.replace("\x1b[4m", "").replace("\x1b[0m", "").split("\t")]
+        k = next(i for i, c in enumerate(cols) if c.startswith("CPU Affinity"))
+        row = next(ln for ln in lines if ln.replace("\x1b[4m", "").startswith(f"GPU{local}\t") or ln.startswith(f"GPU{local} "))
+        aff = [c.strip() for c in row.split("\t")][k]
+        cpus = set()
+        for part in aff.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
+            return aff
+    except Exception:
+        pass
+    return None
+
+
+def load_golden():
+    try:
+        return json.loads((ROOT / "tests" / "golden" / "long_runs.json").read_text())
+    except Exception:
+        return {}
+
+
+def parity_full(np, host_iq, host_pcm, stations, kinds, seconds, budget_s, threads):
+    """Whole-run parity of `host_pcm` [C, n] (int16, what the CUDA path produced for `host_iq`) against
+    (a) the SHA-256 fixtures of tests/golden/long_runs.json (oracle + reference library, precomputed for
+    exactly these bytes) and (b) the oracle C port run live on this box's host cores over every capture
+    (as many as fit `budget_s`).  The oracle is the checker here, nothing else."""
+    import hashlib
+    from concurrent.futures import ThreadPoolExecutor
+    sys.path.insert(0, str(ROOT / "oracle"))
+    golden = load_golden()
+    C = host_iq.shape[0]
+    out = {"captures": C, "seconds_per_capture": seconds}
+
+    def gname(c):
+        if MODE == 0 and TAPS == 51 and abs(seconds - 60.0) < 1e-9:
+            if kinds[c] == "stereo":
+                return f"bench_m0_t51_60s_station{stations[c]}"
+            if stations[c] == 0:
+                return f"hostile_m0_t51_60s_{kinds[c]}"
+        return None
+
+    def hashes(c):
+        return hashlib.sha256(host_iq[c].tobytes()).hexdigest(), hashlib.sha256(host_pcm[c].tobytes()).hexdigest()
+    with ThreadPoolExecutor(threads) as ex:
+        hs = list(ex.map(hashes, range(C)))
+    out["input_sha256"] = hashlib.sha256("".join(h[0] for h in hs).encode()).hexdigest()
+    with_g = [c for c in range(C) if gname(c) in golden]
+    out["golden_captures"] = len(with_g)
+    out["golden_input_identical"] = sum(hs[c][0] == golden[gname(c)]["iq_sha256"] for c in with_g)
+    out["golden_pcm_identical"] = sum(hs[c][1] == golden[gname(c)]["pcm_sha256"] for c in with_g)
+    try:
+        import pyoracle
+        port = pyoracle.Port()
+    except Exception as e:
+        out["oracle"] = f"unavailable ({type(e).__name__})"
+        return out
+    t0 = time.perf_counter()
+
+    def check(c):
+        if time.perf_counter() - t0 > budget_s:
+            return None
+        ref, _ = port.chain(MODE, TAPS).run(host_iq[c])        # ctypes releases the GIL
+        d = np.abs(host_pcm[c].astype(np.int32) - ref.astype(np.int32))
+        nz = np.nonzero(d)[0]
+        return int(len(nz)), int(d.max()) if len(d) else 0, int(nz[0]) if len(nz) else -1
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(check, range(C)))
+    done = [r for r in res if r is not None]
+    out.update({
+        "captures_compared": len(done), "samples_compared": len(done) * int(host_pcm.shape[1]),
+        "samples_differ": sum(r[0] for r in done), "max_abs_lsb": max([r[1] for r in done], default=0),
+        "captures_gt_1lsb": sum(r[1] > 1 for r in done),
+        "first_difference": next(({"capture": c, "pcm_index": r[2]} for c, r in enumerate(res) if r and r[0]), None),
+        "oracle_threads": threads, "oracle_wall_s": round(time.perf_counter() - t0, 1),
+    })
+    return out
+
+
 def main_b200(args):
     import numpy as np
     import torch
@@ -224,6 +318,7 @@ def main_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available() or fm.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    affinity = pin_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -234,18 +329,29 @@ def main_b200(args):
             dist.barrier()
 
     info = fm.mode_table(MODE, TAPS)
-    C = args.captures
+    C = args.captures if not args.strong else max(1, args.captures // world)
     nb = max(1, int(args.seconds * info.rf_fs * 2 / info.block_size))
+    seconds = nb * info.block_size / 2 / info.rf_fs
     n_bytes = nb * info.block_size
     n_pairs = n_bytes // 2
     n_pcm = nb * 2 * info.audio_per_block
     samples_per_step = C * n_pairs                       # per GPU
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
-    # ---- synthetic input, resident in HBM: station k = rank*C + c ----
-    iq = pkg.synth.synth_iq_torch(n_pairs, C, dev, info.rf_fs, first_station=rank * C, seed=1234 + rank)
+    # ---- synthetic input, resident in HBM: station k = rank*C + c (integer synthesiser: the same bytes
+    #      anywhere, tests/golden/long_runs.json holds the reference's PCM hashes for stations 0..63) ----
+    stations = [rank * C + c for c in range(C)]
+    kinds = ["stereo"] * C
+    iq = torch.empty((C, 2 * n_pairs), dtype=torch.uint8, device=dev)
+
+    def synthesise():
+        for c in range(C):
+            pkg.synth.synth_iq_exact_torch(n_pairs, 1, dev, float(info.rf_fs), first_station=stations[c], kinds=[kinds[c]],
+                                           out=iq[c:c + 1])
+        torch.cuda.synchronize()
+    synthesise()
     # PCM is double-buffered so that the gather of step k (NCCL, its own stream) runs under step k+1
     pcm_bufs = [torch.zeros((C, n_pcm), dtype=torch.int16, device=dev) for _ in range(2 if world > 1 else 1)]
-    pcm = pcm_bufs[0]
     gathered = None
     if world > 1 and rank == 0:
         gathered = [torch.empty((C, n_pcm // 2), dtype=torch.int32, device=dev) for _ in range(world)]
@@ -265,78 +371,58 @@ def main_b200(args):
                 pending.pop().wait()                      # receive buffers are about to be reused
             # the only collective: PCM to rank 0 (one R,L frame per int32 word; NCCL has no int16)
             pending.append(dist.gather(buf.view(torch.int32), gathered, dst=0, async_op=True))
+        return buf
 
     def drain():
         while pending:
             pending.pop().wait()
 
-    # ---- parity spot check against the oracle (first capture, first blocks) ----
-    parity = "skipped"
-    if rank == 0:
-        try:
-            sys.path.insert(0, str(ROOT / "oracle"))
-            import pyoracle
-            chk_blocks = min(nb, 64)
-            with fm.Pipeline(MODE, TAPS, 1, device=local) as p1:
-                host_iq = iq[0, :chk_blocks * info.block_size].cpu().numpy()
-                got = p1.process(host_iq)[0]
-            ref, _ = pyoracle.Port().chain(MODE, TAPS).run(host_iq)
-            parity = "bit-identical" if np.array_equal(got, ref) else f"MISMATCH ({int((got != ref).sum())} samples)"
-        except Exception as e:   # the checker is optional at bench time
-            parity = f"unavailable ({type(e).__name__})"
+    def timed_steps(n_steps, with_clocks=False):
+        """n_steps passes, device-timed on `stream` (the pipeline orders its own streams around it), no host
+        synchronisation inside the region; per-kernel times are read from the library's events afterwards."""
+        torch.cuda.synchronize()
+        barrier()
+        pipe.set_timing(True)
+        l0 = pipe.kernel_launches
+        clocks = ClockSampler(local) if with_clocks and rank == 0 else None
+        if clocks:
+            clocks.start()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        barrier()
+        e0.record(stream)
+        last = None
+        for _ in range(n_steps):
+            last = step_device()
+        drain()                                          # the last gather is inside the timed region
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        kern = pipe.last_timing()
+        pipe.set_timing(False)
+        clk = clocks.stop() if clocks else None
+        t_max = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        return float(t_max.item()) / n_steps, {k_: v / n_steps for k_, v in kern.items()}, pipe.kernel_launches - l0, clk, last
 
     # ---- device-resident timing ----
     for _ in range(args.warmup):
         step_device()
     drain()
-    torch.cuda.synchronize()
-    barrier()
-    pipe.set_timing(True)
-    launches0 = pipe.kernel_launches
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    kern = {"rf_demod_ms": 0.0, "bandpass_ms": 0.0, "pll_ms": 0.0, "audio_ms": 0.0}
-    torch.cuda.synchronize()
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        t_host0 = time.perf_counter()
-        step_device()
-        # per-kernel device times of this step (event reads only; the pipeline call above
-        # already made `stream` wait for the step, so this does not add work to the region)
-        torch.cuda.synchronize()
-        t = pipe.last_timing()
-        for k_ in kern:
-            kern[k_] += t[k_]
-        if world > 1:                                    # per-rank step time, for diagnosing a slow rank
-            print(f"[bench rank {rank}] device step {time.perf_counter() - t_host0:.3f} s (k_pll {t['pll_ms']:.0f} ms)",
-                  file=sys.stderr, flush=True)
-    t_host0 = time.perf_counter()
-    drain()                                              # the last gather is inside the timed region
-    if world > 1:
-        print(f"[bench rank {rank}] last gather {time.perf_counter() - t_host0:.3f} s", file=sys.stderr, flush=True)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = pipe.kernel_launches - launches0
-    clk = clocks.stop() if rank == 0 else None
-    pipe.set_timing(False)
-    t_max = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    ms_step = float(t_max.item()) / args.steps
+    ms_step, kern, launches, clk, pcm = timed_steps(args.steps, with_clocks=True)
     value = world * samples_per_step / (ms_step * 1e-3) / 1e6
+    pcm_main = pcm.clone() if world > 1 else pcm          # (double-buffered: keep the last step's result)
 
     # ---- end to end through fmrx_process(): pinned host in, pinned host out ----
     e2e = None
+    h_iq = h_pcm = None
+    e2e_nb = nb
     if not args.no_e2e:
         import psutil
         need = C * n_bytes + C * n_pcm * 2
-        e2e_nb = nb
         avail = psutil.virtual_memory().available / max(1, world)
         if need * 1.3 > avail:                       # not enough host RAM for the full batch
             e2e_nb = max(1, int(nb * avail / (need * 1.3)))
@@ -344,6 +430,22 @@ def main_b200(args):
         h_pcm = torch.empty((C, e2e_nb * 2 * info.audio_per_block), dtype=torch.int16, pin_memory=True)
         h_iq.copy_(iq[:, :e2e_nb * info.block_size])
         torch.cuda.synchronize()
+
+        # what the host link gives this rank while every rank copies at once: plain pinned H2D of the same
+        # buffer (into the resident copy: same bytes), CUDA-event timed
+        link = []
+        for _ in range(2):
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            iq[:, :e2e_nb * info.block_size].copy_(h_iq, non_blocking=True)
+            a1.record(stream)
+            torch.cuda.synchronize()
+            link.append(h_iq.numel() / (a0.elapsed_time(a1) * 1e-3) / 1e9)
+        t_l = torch.tensor([max(link)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_l, op=dist.ReduceOp.SUM)
+        link_total = float(t_l.item())
 
         def step_host():
             pipe.reset()
@@ -360,30 +462,87 @@ def main_b200(args):
         t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        dt = float(t_e.item())
         e2e_samples = C * e2e_nb * info.block_size // 2
-        e2e = {"value": world * e2e_samples * args.steps / float(t_e.item()) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": world * C * e2e_nb * info.block_size,
+        h2d = world * C * e2e_nb * info.block_size
+        e2e = {"value": world * e2e_samples * args.steps / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": world * C * e2e_nb * 2 * info.audio_per_block * 2,
                "seconds_per_capture": e2e_nb * info.block_size / 2 / info.rf_fs,
+               "h2d_gbs": h2d * args.steps / dt / 1e9, "link_ceiling_gbs": link_total,
+               "frac_of_link_ceiling": h2d * args.steps / dt / 1e9 / link_total,
+               "cpu_affinity": affinity,
                "api": "fmrx_process (C ABI, pinned host buffers)"}
-        if rank == 0 and parity == "bit-identical":
-            # the host path must produce the same PCM as the device path
-            same = bool(torch.equal(h_pcm[0], pcm[0, :h_pcm.shape[1]].cpu()))
-            e2e["matches_device_path"] = same
-        del h_iq, h_pcm
+
+    # ---- whole-run parity: every capture, every sample (N=1), or two captures per rank (N>1) ----
+    parity = None
+    if not args.no_parity:
+        n_chk = C if world == 1 else min(C, 2)
+        if h_iq is not None and e2e_nb == nb:
+            host_iq = h_iq.numpy()[:n_chk]
+        else:
+            host_iq = iq[:n_chk].cpu().numpy()
+        host_pcm = pcm_main[:n_chk].cpu().numpy()
+        parity = parity_full(np, host_iq, host_pcm, stations, kinds, seconds, args.parity_budget / (1 if world == 1 else 2),
+                             max(1, cores // (1 if world == 1 else 1)))
+        if h_pcm is not None and e2e_nb == nb:
+            parity["e2e_pcm_identical_to_device_path"] = bool(np.array_equal(h_pcm.numpy()[:n_chk], host_pcm))
+        if world > 1:
+            keys = ("captures", "golden_captures", "golden_input_identical", "golden_pcm_identical", "captures_compared",
+                    "samples_compared", "samples_differ", "captures_gt_1lsb")
+            t = torch.tensor([float(parity.get(k_, 0)) for k_ in keys] + [float(parity.get("max_abs_lsb", 0))],
+                             dtype=torch.float64, device=dev)
+            tm = t[-1:].clone()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            for k_, v in zip(keys, t.tolist()):
+                parity[k_] = int(v)
+            parity["captures"] = n_chk * world
+            parity["max_abs_lsb"] = int(tm.item())
+            parity["note"] = f"{n_chk} captures per rank checked"
+    del h_iq, h_pcm
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        n_proc = max(1, min(cores, C))
+        n_proc = max(1, min(os.cpu_count() or 1, C))
         cpu_blocks = max(8, int(args.cpu_seconds * info.rf_fs * 2 / info.block_size))
         cpu_blocks = min(cpu_blocks, nb)
         sample_iq = iq[0, :cpu_blocks * info.block_size].cpu().numpy().tobytes()
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))      # the baseline gets every core
+        except Exception:
+            pass
         msps, kind, dt = run_cpu_sample(sample_iq, n_proc)
         cpu = {"value": msps, "unit": UNIT, "cores": n_proc, "kind": kind,
                "sample": f"{n_proc} processes x {cpu_blocks * info.block_size / 2 / info.rf_fs:g} s of capture 0 "
                          f"({'reference project binary' if kind == 'reference' else 'oracle C port'}), {dt:.1f} s wall"}
+
+    # ---- data-dependent legs (N=1): the PLL's pace depends on whether its loop is locked ----
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = {}
+        golden = load_golden()
+
+        def leg(name, new_kinds, what):
+            changed = [c for c in range(C) if new_kinds[c] != kinds[c]]
+            for c in changed:
+                kinds[c] = new_kinds[c]
+                pkg.synth.synth_iq_exact_torch(n_pairs, 1, dev, float(info.rf_fs), first_station=stations[c], kinds=[kinds[c]],
+                                               out=iq[c:c + 1])
+            torch.cuda.synchronize()
+            step_device()
+            ms, kk, _, _, out = timed_steps(2)
+            r = {"what": what, "value": samples_per_step / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms,
+                 "pll_ns_per_sample": kk["pll_ms"] * 1e6 / (nb * info.if_per_block),
+                 "vs_all_locked": samples_per_step / (ms * 1e-3) / 1e6 / value}
+            g = golden.get(f"hostile_m0_t51_60s_{kinds[0]}") if kinds[0] != "stereo" else None
+            if g and g["n_blocks"] == nb:
+                import hashlib
+                r["capture0_pcm_identical_to_reference"] = hashlib.sha256(out[0].cpu().numpy().tobytes()).hexdigest() == g["pcm_sha256"]
+            extras[name] = r
+        leg("mixed", ["nopilot"] + ["stereo"] * (C - 1), f"{C - 1} locked captures + 1 without a pilot (its loop never locks)")
+        leg("worst_case", ["noise"] * C, f"{C} noise-only captures (no carrier: no loop ever locks)")
 
     if rank != 0:
         if world > 1:
@@ -399,48 +558,58 @@ def main_b200(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     n_if_step = C * nb * info.if_per_block                          # IF samples per step per GPU
     pll_launches = launches // 4 // max(1, args.steps)              # per step
-    pll_ms_step = kern["pll_ms"] / args.steps
+    pll_ms_step = kern["pll_ms"]
     alg_bytes_launch = 8.0 * n_if_step / max(1, pll_launches)       # 4 B pilot in + 4 B trigArg out per IF sample
     achieved = 8.0 * n_if_step / (pll_ms_step * 1e-3) / 1e9
     traffic = None
     prof = ROOT / "profiles" / "pll_traffic.json"
     if prof.exists():
         traffic = json.loads(prof.read_text())["dram_bytes_per_if_sample"] * n_if_step / max(1, pll_launches)
+    ns_step = pll_ms_step * 1e6 / (nb * info.if_per_block)
+    sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+    cyc_step = ns_step * sm_mhz * 1e-3
     roofline = {"kernel": "k_pll", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "launch_ms": pll_ms_step / max(1, pll_launches),
                 "share_of_step": pll_ms_step / ms_step,
-                "note": "bound by the instruction issue of one warp per capture (one dependent recurrence per capture); see pll_ns_per_sample"}
-    total_k = sum(kern.values()) / args.steps
+                "limiter": "issue",
+                "issue": {"what": "k_pll is one dependent recurrence per capture, run by ONE warp per capture: its bound is that warp's "
+                                  "instruction issue (1 instruction per 2 cycles on this machine), not HBM",
+                          "chain_warp_instructions_per_step": PLL_CHAIN_INSTR_PER_STEP, "cycles_per_step": cyc_step,
+                          "achieved_ipc": PLL_CHAIN_INSTR_PER_STEP / cyc_step, "peak_ipc": 0.5,
+                          "frac": PLL_CHAIN_INSTR_PER_STEP / cyc_step / 0.5, "sm_mhz": sm_mhz},
+                "note": "hbm fraction is tiny by construction; see `issue` and pll_ns_per_sample"}
+    total_k = sum(kern.values())
     # FP32 issue-rate view of the FIR kernels: one MAC = FMUL + FADD (bit-exact, unfused)
     macs_rf = 2.0 * TAPS / info.rf_decim            # per IQ sample (I and Q)
     macs_bp = 2.0 * TAPS / info.rf_decim
     macs_au = 2.0 * TAPS * info.audio_interp / info.audio_decim / info.rf_decim
     fp32_peak_tflops = 148 * 128 * 2 * 1.965e9 / 1e12
+
+    def fir(ms, macs):
+        return {"ms_per_step": ms, "fp32_frac_of_ffma_peak": 2 * macs * samples_per_step / (ms * 1e-3) / 1e12 / fp32_peak_tflops}
     kernels = {
-        "k_rf_demod": {"ms_per_step": kern["rf_demod_ms"] / args.steps,
-                       "fp32_frac_of_ffma_peak": 2 * macs_rf * samples_per_step / (kern["rf_demod_ms"] / args.steps * 1e-3) / 1e12 / fp32_peak_tflops},
-        "k_bandpass_pair": {"ms_per_step": kern["bandpass_ms"] / args.steps,
-                            "fp32_frac_of_ffma_peak": 2 * macs_bp * samples_per_step / (kern["bandpass_ms"] / args.steps * 1e-3) / 1e12 / fp32_peak_tflops},
-        "k_pll": {"ms_per_step": pll_ms_step, "ns_per_if_sample_per_chain": pll_ms_step * 1e6 / (nb * info.if_per_block)},
-        "k_audio": {"ms_per_step": kern["audio_ms"] / args.steps,
-                    "fp32_frac_of_ffma_peak": 2 * macs_au * samples_per_step / (kern["audio_ms"] / args.steps * 1e-3) / 1e12 / fp32_peak_tflops},
+        "k_rf_demod": fir(kern["rf_demod_ms"], macs_rf),
+        "k_bandpass_pair": fir(kern["bandpass_ms"], macs_bp),
+        "k_pll": {"ms_per_step": pll_ms_step, "ns_per_if_sample_per_chain": ns_step},
+        "k_audio": fir(kern["audio_ms"], macs_au),
     }
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(C, nb * info.block_size / 2 / info.rf_fs), "mode": MODE, "taps": TAPS,
+        "config": {"workload": workload_name(C, seconds), "mode": MODE, "taps": TAPS,
                    "captures_per_gpu": C, "blocks_per_capture": nb, "iq_bytes_per_gpu": C * n_bytes,
+                   "input": "integer synthesiser synth.synth_iq_exact_torch, station k = rank*captures_per_gpu + c (SHA-256 in parity_check)",
                    "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"{world} x independent capture shards",
                    "collective": "NCCL gather of PCM to rank 0, step k's gather under step k+1 (all inside the timed region)" if world > 1 else "none"},
         "real_time_factor": value * 1e6 / info.rf_fs,
         "real_time_factor_per_capture": (samples_per_step / C) / (ms_step * 1e-3) / info.rf_fs,
-        "pll_ns_per_sample": kernels["k_pll"]["ns_per_if_sample_per_chain"],
+        "pll_ns_per_sample": ns_step,
         "roofline": roofline, "kernels": kernels, "kernel_ms_per_step_sum": total_k,
         "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches,
-        "parity_check": parity,
+        "parity_check": parity, "extras": extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

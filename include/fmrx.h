@@ -195,9 +195,11 @@ int fmrx_host_free(void *ptr);
 
 /* Kernel launches issued by this pipeline since creation (bench accounting). */
 uint64_t fmrx_kernel_launches(const fmrx_pipeline *p);
-/* Device time of the last fmrx_process* call per kernel family, milliseconds,
- * measured with CUDA events on the launching streams when timing is enabled
- * (fmrx_set_timing(p,1)); out[4] = {rf+demod, band-pass pair, PLL, audio}. */
+/* Device time per kernel family, milliseconds, summed over the fmrx_process*
+ * calls since the previous fmrx_last_timing (or since fmrx_set_timing(p,1)),
+ * measured with CUDA events on the launching streams.  Enabling it adds no
+ * synchronisation to the process calls; fmrx_last_timing itself waits for the
+ * pipeline's streams.  out[4] = {rf+demod, band-pass pair, PLL, audio}. */
 int fmrx_set_timing(fmrx_pipeline *p, int enable);
 int fmrx_last_timing(fmrx_pipeline *p, float out_ms[4]);
 

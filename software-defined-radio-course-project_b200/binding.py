@@ -262,6 +262,8 @@ class Pipeline:
             iq = iq[None, :]
         assert iq.shape[0] == self.n_captures
         nb = iq.shape[1] // self.info.block_size
+        if self.n_captures > 1 and iq.shape[1] != nb * self.info.block_size:
+            iq = np.ascontiguousarray(iq[:, :nb * self.info.block_size])   # rows of whole blocks: an even stride
         pcm = np.zeros((self.n_captures, nb * 2 * self.info.audio_per_block), np.int16)
         self._last_nb = nb
         if nb:

@@ -320,16 +320,19 @@ struct fmrx_pipeline {
     cudaStream_t s_front = nullptr, s_pll = nullptr, s_back = nullptr;
     cudaStream_t s_h2d = nullptr;   // host path: the H2D copies, so that chunk i+1 comes in under K1/K2 of chunk i
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-    long long blocks_done = 0;
+    std::vector<long long> blocks_done;   // per capture: blocks since the start of ITS stream (state blobs carry it)
     long long chunk_counter = 0;
+    size_t mem_pitch = 0;       // cudaDeviceProp::memPitch: the largest pitch cudaMemcpy2D takes
     uint64_t launches = 0;
 
     // keep_stages storage (sized for the last call)
     float *d_stage[FMRX_STAGE_COUNT] = {};
     size_t stage_if_len = 0, stage_au_len = 0;
 
-    // timing
-    std::vector<cudaEvent_t> tev;     // per chunk: 8 events
+    // timing: 8 events per chunk, recorded on the launching streams and only READ when the caller asks
+    // (fmrx_last_timing), so that enabling it adds no synchronisation to fmrx_process_device
+    std::vector<cudaEvent_t> tev;     // event pool
+    size_t tev_used = 0;              // events recorded since the last read
     float last_ms[4] = { 0, 0, 0, 0 };
 };
 
@@ -377,7 +380,7 @@ int reset_state(fmrx_pipeline *p)
         st[8 * c + 4] = 1.0f;   // ncoOut_state
     }
     CU(cudaMemcpy(p->d_pll_state, st.data(), st.size() * sizeof(float), cudaMemcpyHostToDevice));
-    p->blocks_done = 0;
+    p->blocks_done.assign(C, 0);
     return FMRX_OK;
 }
 
@@ -401,14 +404,19 @@ int create_impl(fmrx_pipeline *p, const fmrx_config *cfg)
     if (mi.if_per_block < p->H || mi.block_size / 2 < p->hist_pairs)
         return FMRX_ERR_ARG;
 
-    int cb = cfg->chunk_blocks;
+    // A chunk is one launch of each kernel: its IF samples per capture must stay below 2^26 (k_pll's table
+    // stamps keep the step in 26 bits) and its bytes per capture below 2^31 (int indexing in the FIR kernels).
+    const long long cb_max = std::min<long long>(((1ll << 26) - 1) / mi.if_per_block, ((1ll << 31) - 1) / mi.block_size);
+    if (cb_max < 1)
+        return FMRX_ERR_ARG;
+    int cb = static_cast<int>(std::min<long long>(cfg->chunk_blocks, cb_max));
     if (cb <= 0) {
         // aim at ~128 MiB per IF-rate array per chunk: a K3 launch has to wait for whole SMs to drain
         // of the FIR CTAs of the neighbouring chunks (its CTAs claim a whole SM each), a third of a
         // millisecond that is 12 % of a launch at 32 MiB and 3 % at 128
         const size_t target_if = (128u << 20) / sizeof(float) / C;
         cb = static_cast<int>(std::max<size_t>(1, target_if / mi.if_per_block));
-        cb = std::min(cb, 4096);
+        cb = static_cast<int>(std::min<long long>(std::min(cb, 4096), cb_max));
     }
     p->ramp = cfg->chunk_blocks <= 0;
     p->chunk_blocks = cb;
@@ -499,8 +507,19 @@ int ensure_stage_storage(fmrx_pipeline *p, size_t n_blocks)
 
 // Copy `rows` rows of `width` bytes between pitched device arrays.
 cudaError_t copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width,
-                   size_t rows, cudaStream_t s, cudaMemcpyKind kind = cudaMemcpyDeviceToDevice)
+                   size_t rows, cudaStream_t s, cudaMemcpyKind kind = cudaMemcpyDeviceToDevice, size_t max_pitch = 0)
 {
+    // one row, or a pitch beyond what cudaMemcpy2D takes (cudaDeviceProp::memPitch, ~2 GiB: 7.5 minutes
+    // of mode-0 IQ per capture): plain copies, row by row
+    if (rows == 1 || (max_pitch && (dpitch > max_pitch || spitch > max_pitch))) {
+        for (size_t r = 0; r < rows; r++) {
+            cudaError_t e = cudaMemcpyAsync(static_cast<char *>(dst) + r * dpitch, static_cast<const char *>(src) + r * spitch,
+                                            width, kind, s);
+            if (e != cudaSuccess)
+                return e;
+        }
+        return cudaSuccess;
+    }
     return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, s);
 }
 
@@ -544,12 +563,13 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
     }
     const size_t n_chunks = chunk_nb.size();
     if (p->timing) {
-        while (p->tev.size() < 8 * n_chunks) {
+        while (p->tev.size() < p->tev_used + 8 * n_chunks) {
             cudaEvent_t e;
             CU(cudaEventCreate(&e));
             p->tev.push_back(e);
         }
     }
+    const size_t tev0 = p->tev_used;
 
     size_t b_next = 0;
     for (size_t ci = 0; ci < n_chunks; ci++) {
@@ -560,7 +580,7 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
         const size_t chunk_bytes = static_cast<size_t>(nb) * mi.block_size;
         const size_t chunk_pcm = static_cast<size_t>(nb) * 2 * mi.audio_per_block;
         BufferSet &S = p->sets[p->chunk_counter % kSets];
-        cudaEvent_t *te = p->timing ? &p->tev[8 * ci] : nullptr;
+        cudaEvent_t *te = p->timing ? &p->tev[tev0 + 8 * ci] : nullptr;
 
         // ---------------- front: [H2D] K1 K2 ----------------
         if (S.free_pending)
@@ -575,7 +595,7 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
             if (S.iq_free_pending)
                 CU(cudaStreamWaitEvent(p->s_h2d, S.iq_free, 0));
             CU(copy2d(S.iq, iq_dev_stride, iq + b0 * mi.block_size, iq_stride, chunk_bytes, C,
-                      p->s_h2d, cudaMemcpyHostToDevice));
+                      p->s_h2d, cudaMemcpyHostToDevice, p->mem_pitch));
             CU(cudaEventRecord(S.h2d_done, p->s_h2d));
             CU(cudaStreamWaitEvent(p->s_front, S.h2d_done, 0));
         } else {
@@ -675,7 +695,6 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
             a.if_per_block = mi.if_per_block;
             a.audio_per_block = mi.audio_per_block;
             a.n_blocks = nb;
-            a.first_block = p->blocks_done;
             a.scale = p->pll_prm.scale;
             a.adjust = p->pll_prm.adjust;
             if (host_io) {
@@ -715,12 +734,13 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
         if (host_io)
             CU(copy2d(pcm + b0 * 2 * mi.audio_per_block, pcm_stride * sizeof(int16_t), S.pcm,
                       static_cast<size_t>(p->chunk_blocks) * 2 * mi.audio_per_block * sizeof(int16_t),
-                      chunk_pcm * sizeof(int16_t), C, p->s_back, cudaMemcpyDeviceToHost));
+                      chunk_pcm * sizeof(int16_t), C, p->s_back, cudaMemcpyDeviceToHost, p->mem_pitch));
         if (te) CU(cudaEventRecord(te[7], p->s_back));
         CU(cudaEventRecord(S.free_ev, p->s_back));
         S.free_pending = true;
 
-        p->blocks_done += nb;
+        for (auto &bd : p->blocks_done)
+            bd += nb;
         p->chunk_counter++;
     }
 
@@ -736,20 +756,8 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
         CU(cudaEventRecord(p->ev_out, p->s_front));
         CU(cudaStreamWaitEvent(user, p->ev_out, 0));
     }
-    if (p->timing) {
-        CU(cudaStreamSynchronize(p->s_back));
-        CU(cudaStreamSynchronize(p->s_front));
-        float acc[4] = { 0, 0, 0, 0 };
-        for (size_t ci = 0; ci < n_chunks; ci++) {
-            cudaEvent_t *te = &p->tev[8 * ci];
-            float ms = 0;
-            CU(cudaEventElapsedTime(&ms, te[0], te[1])); acc[0] += ms;
-            CU(cudaEventElapsedTime(&ms, te[1], te[2])); acc[1] += ms;
-            CU(cudaEventElapsedTime(&ms, te[3], te[4])); acc[2] += ms;
-            CU(cudaEventElapsedTime(&ms, te[5], te[6])); acc[3] += ms;
-        }
-        std::memcpy(p->last_ms, acc, sizeof(acc));
-    }
+    if (p->timing)
+        p->tev_used = tev0 + 8 * n_chunks;
     return FMRX_OK;
 }
 
@@ -760,12 +768,12 @@ int check_io(const fmrx_pipeline *p, const void *iq, size_t iq_stride, size_t n_
         return FMRX_ERR_ARG;
     const size_t need_iq = n_blocks * p->mi.block_size;
     const size_t need_pcm = n_blocks * 2 * p->mi.audio_per_block;
-    if (p->C > 1 && (iq_stride < need_iq || pcm_stride < need_pcm))
-        return FMRX_ERR_ARG;
     // K1 reads IQ pairs as 16-bit words, K4 writes R,L frames as 32-bit words
-    if ((reinterpret_cast<uintptr_t>(iq) | iq_stride) & 1u)
+    if ((reinterpret_cast<uintptr_t>(iq) & 1u) || (reinterpret_cast<uintptr_t>(pcm) & 3u))
         return FMRX_ERR_ARG;
-    if ((reinterpret_cast<uintptr_t>(pcm) & 3u) || (pcm_stride & 1u))
+    // the strides only matter with more than one capture (a single capture may be a truncated file of
+    // any length: the trailing partial block is the caller's to drop)
+    if (p->C > 1 && (iq_stride < need_iq || pcm_stride < need_pcm || (iq_stride & 1u) || (pcm_stride & 1u)))
         return FMRX_ERR_ARG;
     return FMRX_OK;
 }
@@ -774,7 +782,7 @@ int check_io(const fmrx_pipeline *p, const void *iq, size_t iq_stride, size_t n_
 
 extern "C" int fmrx_create(fmrx_pipeline **out, const fmrx_config *cfg)
 {
-    if (!out || !cfg || cfg->n_captures < 1)
+    if (!out || !cfg || cfg->n_captures < 1 || cfg->n_captures > 65535)   // captures are gridDim.y of K1, K2, K4
         return FMRX_ERR_ARG;
     for (int r : cfg->reserved)
         if (r != 0)
@@ -803,6 +811,7 @@ extern "C" int fmrx_create(fmrx_pipeline **out, const fmrx_config *cfg)
         return FMRX_ERR_ALLOC;
     p->mi = mi;
     p->device = dev;
+    p->mem_pitch = prop.memPitch;
     const int rc = create_impl(p, cfg);
     if (rc != FMRX_OK) {
         free_pipeline(p);
@@ -844,6 +853,10 @@ extern "C" int fmrx_process(fmrx_pipeline *p, const uint8_t *iq, size_t iq_strid
     if (rc != FMRX_OK)
         return rc;
     CU(cudaSetDevice(p->device));
+    if (p->C == 1) {
+        iq_stride = n_blocks * p->mi.block_size;
+        pcm_stride = n_blocks * 2 * p->mi.audio_per_block;
+    }
     return run(p, iq, iq_stride, n_blocks, pcm, pcm_stride, true, nullptr);
 }
 
@@ -856,6 +869,10 @@ extern "C" int fmrx_process_device(fmrx_pipeline *p, const uint8_t *iq_dev, size
     if (rc != FMRX_OK)
         return rc;
     CU(cudaSetDevice(p->device));
+    if (p->C == 1) {
+        iq_stride = n_blocks * p->mi.block_size;
+        pcm_stride = n_blocks * 2 * p->mi.audio_per_block;
+    }
     return run(p, iq_dev, iq_stride, n_blocks, pcm_dev, pcm_stride, false,
                static_cast<cudaStream_t>(stream));
 }
@@ -896,7 +913,7 @@ extern "C" int fmrx_get_state(fmrx_pipeline *p, int capture, void *blob, size_t 
     uint8_t *b = static_cast<uint8_t *>(blob);
     std::memset(b, 0, fmrx_state_size(p));
     StateHeader h{ kStateMagic, static_cast<uint32_t>(p->mi.mode), static_cast<uint32_t>(p->mi.taps),
-                   static_cast<uint32_t>(p->H), static_cast<uint32_t>(p->hist_pairs), 0, p->blocks_done };
+                   static_cast<uint32_t>(p->H), static_cast<uint32_t>(p->hist_pairs), 0, p->blocks_done[capture] };
     std::memcpy(b, &h, sizeof(h));
     b += sizeof(h);
     const size_t iqb = 2 * static_cast<size_t>(p->hist_pairs);
@@ -949,7 +966,7 @@ extern "C" int fmrx_set_state(fmrx_pipeline *p, int capture, const void *blob, s
                       cudaMemcpyHostToDevice));
         CU(cudaMemcpy(p->d_pll_state + 8 * static_cast<size_t>(capture), b_pll, 8 * sizeof(float),
                       cudaMemcpyHostToDevice));
-        p->blocks_done = h.blocks_done;
+        p->blocks_done[capture] = h.blocks_done;
     }
     return FMRX_OK;
 }
@@ -974,6 +991,7 @@ extern "C" int fmrx_set_timing(fmrx_pipeline *p, int enable)
     if (!p)
         return FMRX_ERR_ARG;
     p->timing = enable != 0;
+    p->tev_used = 0;
     return FMRX_OK;
 }
 
@@ -981,6 +999,23 @@ extern "C" int fmrx_last_timing(fmrx_pipeline *p, float out_ms[4])
 {
     if (!p || !out_ms)
         return FMRX_ERR_ARG;
+    if (p->tev_used) {
+        CU(cudaSetDevice(p->device));
+        CU(cudaStreamSynchronize(p->s_back));
+        CU(cudaStreamSynchronize(p->s_pll));
+        CU(cudaStreamSynchronize(p->s_front));
+        float acc[4] = { 0, 0, 0, 0 };
+        for (size_t i = 0; i < p->tev_used; i += 8) {
+            cudaEvent_t *te = &p->tev[i];
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, te[0], te[1])); acc[0] += ms;
+            CU(cudaEventElapsedTime(&ms, te[1], te[2])); acc[1] += ms;
+            CU(cudaEventElapsedTime(&ms, te[3], te[4])); acc[2] += ms;
+            CU(cudaEventElapsedTime(&ms, te[5], te[6])); acc[3] += ms;
+        }
+        std::memcpy(p->last_ms, acc, sizeof(acc));
+        p->tev_used = 0;
+    }
     std::memcpy(out_ms, p->last_ms, sizeof(p->last_ms));
     return FMRX_OK;
 }

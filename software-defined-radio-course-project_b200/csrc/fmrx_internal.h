@@ -71,7 +71,6 @@ struct AudioArgs {
     int T, U, D;
     int if_per_block, audio_per_block;
     int n_blocks;           // blocks in this chunk
-    long long first_block;  // global index of the chunk's first block (0 = start of capture)
     float scale, adjust;    // NCO parameters (2, 0)
     int16_t *pcm;           // capture c at pcm + c*pcm_stride; frame g at [2g],[2g+1] = R,L
     size_t pcm_stride;

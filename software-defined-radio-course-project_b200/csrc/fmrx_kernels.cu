@@ -16,12 +16,36 @@
 // FIR arithmetic is acc = fadd(acc, fmul(c[k], x)) from +0 with k ascending --
 // the reference's exact sequence -- so one MAC costs an FMUL and an FADD: the
 // attainable ceiling of these kernels is half the FFMA peak by construction.
+#include <mutex>
+
 #include "fmrx_internal.h"
 #ifdef FMRX_PLL_PROFILE   // development build: k_pll prints its cycle accounting for capture 0 of every launch
 #include <cstdio>
 #endif
 
 namespace fmrx {
+
+// Per-device launch configuration.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to
+// the CURRENT device only, and one process may hold pipelines on several devices
+// (fmrx_config.device), created from several host threads: everything cached about a kernel's
+// opt-in shared memory is keyed by the device ordinal and guarded by a mutex.
+constexpr int kMaxDevices = 64;
+struct DeviceCfg {
+    size_t rf_smem[3] = { 0, 0, 0 };       // k_rf_demod_win<10>, <4>, <9>: configured dynamic shared memory
+    size_t audio_smem = 0;                 // k_audio
+    size_t bp_smem = 0;                    // k_bandpass_pair
+    size_t pll_ring_only = 0, pll_whole_sm = 0;
+    int sm_count = 0;
+};
+static std::mutex g_cfg_mutex;
+static DeviceCfg g_cfg[kMaxDevices];
+static DeviceCfg *device_cfg()
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices)
+        return nullptr;
+    return &g_cfg[dev];
+}
 
 // ============================================================================
 // K1: u8 unpack + RF FIR (decimating) + FM discriminator
@@ -30,116 +54,10 @@ namespace fmrx {
 // A tile computes RF_COMPUTED consecutive IF outputs; the first one is the
 // discriminator's "previous sample" halo, so RF_COMPUTED-1 demod samples are
 // produced.  The u8 IQ window of the tile is converted to float ONCE while it
-// is staged into shared memory, de-interleaved into an I plane and a Q plane,
-// each stored phase-major (index m -> row m%decim, column m/decim): output o
-// reads x[o*decim + e] = row e%decim, column o + e/decim, so the 32 lanes of a
-// warp (consecutive o) hit consecutive banks for any decimation factor.
+// is staged into shared memory, de-interleaved into an I plane and a Q plane.
 
-constexpr int RF_THREADS = 256;
-constexpr int RF_R = 2;                                 // outputs per thread
-constexpr int RF_COMPUTED = RF_THREADS * RF_R;          // 512
+constexpr int RF_COMPUTED = 512;                        // IF outputs computed per tile
 constexpr int RF_REAL = RF_COMPUTED - 1;                // 511 demod samples per tile
-
-static inline int rf_row_stride(int T, int decim)
-{
-    const int cols = RF_COMPUTED + (T + decim - 1) / decim + 1;
-    const int want = (32 + decim - 1) / decim;          // spreads the staging stores over banks
-    int rs = cols;
-    while ((rs & 31) != (want & 31))
-        rs++;
-    return rs;
-}
-
-static inline size_t rf_smem_bytes(int T, int decim)
-{
-    return sizeof(float) * ((size_t)2 * decim * rf_row_stride(T, decim) + 2 * RF_COMPUTED + T);
-}
-
-__global__ void __launch_bounds__(RF_THREADS) k_rf_demod(const RfDemodArgs a, const int rs)
-{
-    extern __shared__ float smem[];
-    const int T = a.T, d = a.decim;
-    float *s_i = smem;                       // [d][rs]
-    float *s_q = s_i + d * rs;               // [d][rs]
-    float *o_i = s_q + d * rs;               // [RF_COMPUTED]
-    float *o_q = o_i + RF_COMPUTED;
-    float *s_c = o_q + RF_COMPUTED;          // [T]
-
-    const int c = blockIdx.y;
-    const int tid = threadIdx.x;
-    const int n0 = blockIdx.x * RF_REAL;     // first demod sample of the tile
-    const long long n_pairs = (long long)a.n_if * d;
-    // chunk-local pair index of staged element l:  m = m_base + l
-    const long long m_base = (long long)(n0 - 1) * d - (T - 1);
-    const int W = (RF_COMPUTED - 1) * d + T;
-
-    const uint8_t *iq = a.iq + (size_t)c * a.iq_stride;
-    const uint8_t *hist = a.hist + (size_t)c * 2 * a.hist_pairs;
-
-    for (int k = tid; k < T; k += RF_THREADS)
-        s_c[k] = a.taps[k];
-
-    for (int l = tid; l < W; l += RF_THREADS) {
-        const long long m = m_base + l;
-        uint32_t v = 0x8080u;                // (128,128) -> 0.0f, 0.0f
-        if (m >= 0) {
-            if (m < n_pairs)
-                v = *reinterpret_cast<const uint16_t *>(iq + 2 * m);
-        } else {
-            const long long h = a.hist_pairs + m;
-            if (h >= 0)
-                v = *reinterpret_cast<const uint16_t *>(hist + 2 * h);
-        }
-        const int row = l % d, col = l / d;
-        s_i[row * rs + col] = unpack_u8(v & 0xffu);
-        s_q[row * rs + col] = unpack_u8(v >> 8);
-    }
-    __syncthreads();
-
-    float acc_i[RF_R], acc_q[RF_R];
-#pragma unroll
-    for (int r = 0; r < RF_R; r++) {
-        acc_i[r] = 0.0f;
-        acc_q[r] = 0.0f;
-    }
-    // tap k multiplies x[o*d + (T-1-k)]
-    int e = T - 1;
-    int row = e % d, cb = e / d;
-    for (int k = 0; k < T; k++) {
-        const float ck = s_c[k];
-        const int idx = row * rs + cb + tid;
-#pragma unroll
-        for (int r = 0; r < RF_R; r++) {
-            acc_i[r] = fadd(acc_i[r], fmul(ck, s_i[idx + r * RF_THREADS]));
-            acc_q[r] = fadd(acc_q[r], fmul(ck, s_q[idx + r * RF_THREADS]));
-        }
-        if (--row < 0) {
-            row = d - 1;
-            cb--;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < RF_R; r++) {
-        o_i[tid + r * RF_THREADS] = acc_i[r];
-        o_q[tid + r * RF_THREADS] = acc_q[r];
-    }
-    __syncthreads();
-
-    float *demod = a.demod + (size_t)c * a.if_stride + a.if_off;
-#pragma unroll
-    for (int r = 0; r < RF_R; r++) {
-        const int o = tid + r * RF_THREADS;
-        const int n = n0 - 1 + o;
-        if (o >= 1 && n < a.n_if) {
-            demod[n] = fm_discriminate(o_i[o], o_q[o], o_i[o - 1], o_q[o - 1]);
-            if (a.i_ds) {
-                const size_t g = (size_t)c * a.stage_stride + a.stage_off + n;
-                a.i_ds[g] = o_i[o];
-                a.q_ds[g] = o_q[o];
-            }
-        }
-    }
-}
 
 // ---- K1, register-window version (decimation known at compile time) ----------------
 //
@@ -309,13 +227,19 @@ template <int D> __global__ void __launch_bounds__(RFW_THREADS) k_rf_demod_win(c
 
 template <int D> static cudaError_t launch_rf_demod_win(const RfDemodArgs &a, int n_captures, cudaStream_t s)
 {
-    static size_t configured = 0;
     const size_t smem = RfWin<D>::smem_bytes(a.T);
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_rf_demod_win<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-            return e;
-        configured = smem;
+    DeviceCfg *cfg = device_cfg();
+    if (!cfg)
+        return cudaErrorInvalidDevice;
+    {
+        std::lock_guard<std::mutex> lock(g_cfg_mutex);
+        size_t &configured = cfg->rf_smem[D == 10 ? 0 : D == 4 ? 1 : 2];
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(k_rf_demod_win<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess)
+                return e;
+            configured = smem;
+        }
     }
     const int tiles = (a.n_if + RF_REAL - 1) / RF_REAL;
     dim3 grid(tiles, n_captures);
@@ -325,26 +249,14 @@ template <int D> static cudaError_t launch_rf_demod_win(const RfDemodArgs &a, in
 
 cudaError_t launch_rf_demod(const RfDemodArgs &a, int n_captures, cudaStream_t s)
 {
-    // the reference's modes decimate by 10, 4 and 9 (src/project.cpp:327-362)
+    // the reference's modes decimate by 10, 4 and 9 (src/project.cpp:327-362); fmrx_mode_table yields nothing else
     if (a.decim == 10)
         return launch_rf_demod_win<10>(a, n_captures, s);
     if (a.decim == 4)
         return launch_rf_demod_win<4>(a, n_captures, s);
     if (a.decim == 9)
         return launch_rf_demod_win<9>(a, n_captures, s);
-    static size_t configured = 0;
-    const size_t smem = rf_smem_bytes(a.T, a.decim);
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_rf_demod, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess)
-            return e;
-        configured = smem;
-    }
-    const int tiles = (a.n_if + RF_REAL - 1) / RF_REAL;
-    dim3 grid(tiles, n_captures);
-    k_rf_demod<<<grid, RF_THREADS, smem, s>>>(a, rf_row_stride(a.T, a.decim));
-    return cudaGetLastError();
+    return cudaErrorInvalidValue;
 }
 
 // ============================================================================
@@ -679,12 +591,19 @@ __device__ __noinline__ void pll_group_checked(pllcore::Chain &chain, const pllc
 // instruction of a candidate warp (four lanes, 8 bytes each), read by warp 0 as two
 // 16-byte halves -- the half with the key and the block stamp FIRST, so that a half
 // overwritten in between can only fail the check, never pass it.
+// The stamp of a table: which block of 16 steps of the launch it is for (low 26 bits: a launch has
+// fewer than 2^26 steps, fmrx_create sees to that) and the low 6 bits of the block pi its threshold
+// was formed with -- warp 0 and the candidate warps each from their OWN pi, so a disagreement about
+// pi (tests/pll_model.cpp, pll_model_stale_head) fails the stamp check instead of selecting a
+// neighbouring hypothesis silently.  Never 0 (the stamp of an invalidated row).
+__device__ __forceinline__ int pll_stamp(int u0, int kbase) { return (u0 + 1) ^ (kbase << 26); }
+
 struct __align__(32) PllRow {
     float kpe0, kie0, kpe1, kie1;    // Kp*errorD, Ki*errorD of the next sample if trigArg is grid point G_c - 1, G_c
     float kpe2, kie2;                // ... G_c + 1
     float lp;                        // (n1 - 1/2) - vr, n1 = G_c - (vi + pi): trigArg IS G_c iff lp < t < lp + 1,
                                      // t = fma(phaseEst, 1/ulp, -pi) as warp 0 computes it (PLL_ROW_INVALID if a guard failed)
-    int stamp;                       // (step & ~15) + 1: which block of 16 steps of the launch the table is for
+    int stamp;                       // pll_stamp(step & ~15, kbase of that block)
 };
 
 __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
@@ -840,7 +759,7 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
         // of 16 and u0 is one): addresses are base + constant
         const unsigned in_a0 = in_base + (unsigned)(u0 & (PLL_RING - 1)) * (unsigned)sizeof(PllIn);
         const unsigned tab_a0 = tab_base + (unsigned)(u0 & (PLL_TABLES - 1)) * (unsigned)sizeof(PllRow);
-        const int stamp = u0 + 1;
+        const int stamp = pll_stamp(u0, kbase);
         int gis[16];
         // tables are fetched two steps ahead -- late enough for the candidate warps, early enough
         // to be off the chain; the half of a table with the stamp before its other half
@@ -871,6 +790,16 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(gis[j]), "r"(gis[j + 1]),
                          "r"(gis[j + 2]), "r"(gis[j + 3])
                          : "memory");
+        // The 16 stamps once more, lane j that of row j: a row is read as two halves (stamp half first),
+        // so a row REPLACED between the two loads -- by a candidate warp that fell a whole ring behind
+        // and stores the table of step u - PLL_TABLES late -- would pass the first check with the other
+        // step's data.  Any store to a row changes its stamp (one stamp per step block and pi), so the
+        // stamp still being there now means both halves were this block's.
+        {
+            int z;
+            asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(z) : "r"(tab_a0 + (unsigned)(lane & 15) * (unsigned)sizeof(PllRow) + 28u) : "memory");
+            bad |= __any_sync(0xffffffffu, z != stamp);
+        }
         if (!settle(u0, 16, integ0, ph0, gi0) || n_exact > PLL_EXACT_MAX) {
             fatal = true;            // (more exact blocks than a group without tables costs: give the group up)
             break;
@@ -891,9 +820,15 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
             const unsigned row = tab_base + (unsigned)(u & (PLL_TABLES - 1)) * (unsigned)sizeof(PllRow);
             const int4 rb = load_half(row + 16u), ra = load_half(row);
             const int2 vg = load_vg(in_base + (unsigned)(u & (PLL_RING - 1)) * (unsigned)sizeof(PllIn));
-            const int tb = step(ra, rb, u0 + 1, j == nb - 1);
+            const int tb = step(ra, rb, pll_stamp(u0, kbase), j == nb - 1);
             gi = vg.x + kbase + __float_as_int(p_faddf(p_faddf(__int_as_float(tb), __int_as_float(vg.y)), 12582912.0f));
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(tb) : "memory");
+        }
+        {   // the stamps once more (see the full blocks)
+            int z = pll_stamp(u0, kbase);
+            if (lane < nb)
+                asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(z) : "r"(tab_base + (unsigned)((u0 + lane) & (PLL_TABLES - 1)) * (unsigned)sizeof(PllRow) + 28u) : "memory");
+            bad |= __any_sync(0xffffffffu, z != pll_stamp(u0, kbase));
         }
         fatal = !settle(u0, nb, integ0, ph0, gi0);
     }
@@ -1028,12 +963,12 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             // its possible values lie a whole phaseEst spacing (thousands of its own grid steps) apart:
             // no tables there.
             const bool spec = regular && !dead && skip == 0 && ch.binade != FMRX_DISARMED &&
-                              s_prep_ulp[g & 3] == ch.ulp && (double)fabsf(ch.ph) < ch.ulp * 16777216.0 &&
-                              t0 + base + cnt < 16777216;
-            // (no tables once trigOffset sits at 2^24 either: a 288 kHz loop run on tables past that point came
-            // out different from the reference in 1.4 % of its trigArgs -- tests/test_gpu_operators.py::
-            // test_pll_long_run_past_counter_saturation.  The cause is the stale head dealt with just below;
-            // the restriction stays until that fix has been run on a GPU: DESIGN.md section 6 and 9.)
+                              s_prep_ulp[g & 3] == ch.ulp && (double)fabsf(ch.ph) < ch.ulp * 16777216.0;
+            // (Tables also serve the regime past trigOffset == 2^24, where trigArg freezes on two grid points
+            // and the loop dithers across a float rounding boundary: tests/test_gpu_operators.py::
+            // test_pll_long_run_past_counter_saturation and the >= 70 s pipeline runs of
+            // tests/test_gpu_long_runs.py.  Round 1 kept them off there until the stale-head fix just
+            // below had been run on a GPU.)
 
             // the group before ran on tables to its end and hardly needed the exact step: predictor and
             // candidates did our head, and the predictor carries on from its own state (otherwise it
@@ -1108,7 +1043,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     int spin = 0;
                     for (;;) {
                         const int z = ld_v4(&s_tab[(base + (lane & 15)) & (PLL_TABLES - 1)].kpe2).w;      // the stamp
-                        if (__all_sync(0xffffffffu, !need || z == base + 1) || ++spin >= PLL_SPIN_LIMIT)
+                        if (__all_sync(0xffffffffu, !need || (z & 0x3ffffff) == base + 1) || ++spin >= PLL_SPIN_LIMIT)
                             break;
                     }
                     if (spin >= PLL_SPIN_LIMIT) {
@@ -1302,10 +1237,13 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                         break;
                     }
                     // one store instruction writes the eight tables: 8 bytes per lane, 32 per quad
-                    if (live) {
+                    // (a warp that fell so far behind that warp 0 has already left this batch behind -- it
+                    // stepped those blocks the exact way -- must not store: the rows may by now belong to the
+                    // steps one ring further on)
+                    if (live && prog - (ub8 + PLL_BATCH) < 0) {
                         const int lo = jq < 3 ? __float_as_int(p_fmulf(k.kp, ed))
                                               : __float_as_int(valid ? p_faddf(p_faddf((float)n1, -0.5f), -vr) : PLL_ROW_INVALID);
-                        const int hi = jq < 3 ? __float_as_int(p_fmulf(k.ki, ed)) : (u & ~15) + 1;
+                        const int hi = jq < 3 ? __float_as_int(p_fmulf(k.ki, ed)) : pll_stamp(u & ~15, kb);
                         asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(smem_u32(&s_tab[u & (PLL_TABLES - 1)]) + 8u * (unsigned)jq),
                                      "r"(lo), "r"(hi)
                                      : "memory");
@@ -1423,29 +1361,39 @@ cudaError_t launch_pll(const PllArgs &a_in, int n_captures, cudaStream_t s)
     // to spare, a PLL CTA therefore claims the whole shared memory of its SM, which keeps
     // every other CTA off it.  With more captures than that leaves SMs for, it only asks
     // for the ring it needs and shares.
-    static size_t ring_only = 0, whole_sm = 0;
-    static int sm_count = 0;
-    if (ring_only == 0) {
-        int dev = 0, optin = 0;
-        cudaFuncAttributes fa;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess)
-            e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (e == cudaSuccess)
-            e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess)
-            e = cudaFuncGetAttributes(&fa, k_pll);
-        if (e != cudaSuccess)
-            return e;
-        const size_t need = sizeof(PllIn) * PLL_RING;
-        size_t all = (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : 0;
-        if (all < need)
-            all = need;
-        e = cudaFuncSetAttribute(k_pll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)all);
-        if (e != cudaSuccess)
-            return e;
-        whole_sm = all;
-        ring_only = need;
+    DeviceCfg *cfg = device_cfg();
+    if (!cfg)
+        return cudaErrorInvalidDevice;
+    size_t ring_only, whole_sm;
+    int sm_count;
+    {
+        std::lock_guard<std::mutex> lock(g_cfg_mutex);
+        if (cfg->pll_ring_only == 0) {
+            int dev = 0, optin = 0, sms = 0;
+            cudaFuncAttributes fa;
+            cudaError_t e = cudaGetDevice(&dev);
+            if (e == cudaSuccess)
+                e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            if (e == cudaSuccess)
+                e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (e == cudaSuccess)
+                e = cudaFuncGetAttributes(&fa, k_pll);
+            if (e != cudaSuccess)
+                return e;
+            const size_t need = sizeof(PllIn) * PLL_RING;
+            size_t all = (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : 0;
+            if (all < need)
+                all = need;
+            e = cudaFuncSetAttribute(k_pll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)all);
+            if (e != cudaSuccess)
+                return e;
+            cfg->pll_whole_sm = all;
+            cfg->pll_ring_only = need;
+            cfg->sm_count = sms;
+        }
+        ring_only = cfg->pll_ring_only;
+        whole_sm = cfg->pll_whole_sm;
+        sm_count = cfg->sm_count;
     }
     const bool isolate = n_captures + kPllSpareSms <= sm_count;
     k_pll<<<n_captures, PLL_THREADS, isolate ? whole_sm : ring_only, s>>>(a);

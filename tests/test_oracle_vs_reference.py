@@ -100,7 +100,8 @@ def test_chain_all_stages_bitwise(port, reference, synth, mode, taps, nblocks):
 @pytest.mark.parametrize("taps", [51, 101])
 def test_reference_binary_pcm_is_prefix(port, synth, taps):
     """End to end against the reference's own `project` binary: its stdout is an exact
-    prefix of the oracle's PCM, short by the <=4 blocks it loses at EOF."""
+    prefix of the oracle's PCM, short by the 0..4 blocks it loses at EOF (a race between
+    its two threads at exit, so how many -- possibly none -- varies from run to run)."""
     exe = pyoracle.Reference.binary(taps)
     if exe is None:
         pytest.skip("reference binary not built")
@@ -111,7 +112,7 @@ def test_reference_binary_pcm_is_prefix(port, synth, taps):
     out = np.frombuffer(r.stdout, np.int16)
     pcm, _ = port.chain(0, taps).run(iq)
     per_block = 2 * info.audio_per_block
-    assert len(out) % per_block == 0 and 0 < len(pcm) - len(out) <= 4 * per_block
+    assert len(out) % per_block == 0 and 0 <= len(pcm) - len(out) <= 4 * per_block
     assert np.array_equal(out, pcm[:len(out)])
 
 

@@ -1,16 +1,16 @@
 #!/usr/bin/env python
-"""Device-resident throughput of the chain on every BASELINE.json configuration that is
-not the bench workload (bench.py times configs[3]; these are the parity-test cases):
-one JSON line per configuration, CUDA-event timed, synthetic IQ generated on the GPU.
+"""Device-resident throughput AND whole-run parity of the chain on every BASELINE.json
+configuration that is not the bench workload (bench.py times configs[3]): one JSON line per
+configuration, CUDA-event timed, the capture made on the GPU by the integer synthesiser and the
+complete PCM compared by SHA-256 with the reference's (tests/golden/long_runs.json: oracle port
+and the reference's own compiled filter.cpp, precomputed for exactly these bytes).
 
-    python tools/config_sweep.py [--hour-seconds 3600] > gpurun_out/config_sweep.jsonl
-
-Every line also carries a parity spot check of the first blocks against the oracle
-(checker only) and the per-kernel device times of the pass.
+    python tools/config_sweep.py [--only name,name] > gpurun_out/config_sweep.jsonl
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import importlib
 import json
 import sys
@@ -18,12 +18,10 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "oracle"))
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--hour-seconds", type=float, default=3600.0, help="length of the configs[4] capture")
     ap.add_argument("--only", default="", help="comma-separated config names")
     args = ap.parse_args()
 
@@ -36,34 +34,39 @@ def main():
         raise SystemExit("config_sweep.py: no CUDA device -- the product path has no CPU fallback")
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    try:
-        import pyoracle
-        port = pyoracle.Port()
-    except Exception:
-        port = None
+    golden = json.loads((ROOT / "tests" / "golden" / "long_runs.json").read_text())
 
-    # name, BASELINE.json config, mode, taps, captures, seconds
+    # name, BASELINE.json config, golden fixture(s) (one per capture)
     cases = [
-        ("m0_t101_1x60s", "configs[0] mode 0 mono, 101 taps (the reference ignores `channels`: same R,L stream)", 0, 101, 1, 60.0),
-        ("m0_t51_1x60s", "configs[1] mode 0 stereo, 51 taps, one capture", 0, 51, 1, 60.0),
-        ("m1_t51_1x120s", "mode 1 (1.44 Msps, decim 4), 51 taps, one capture", 1, 51, 1, 120.0),
-        ("m2_t51_1x120s", "configs[2] mode 2 (147/800 polyphase to 44.1 kHz), 51 taps, one capture", 2, 51, 1, 120.0),
-        ("m3_t51_1x120s", "configs[2] mode 3 (2.304 Msps, 441/2560 polyphase), 51 taps, one capture", 3, 51, 1, 120.0),
-        ("m0_t301_64x8s", "mode 0, 301 taps, 64 captures x 8 s (FIR-heavy case)", 0, 301, 64, 8.0),
-        ("m0_t301_1hour", f"configs[4] one {args.hour_seconds:g} s capture, 301 taps, on one GPU "
-                          "(the PLL is one chain: time shards on more GPUs add capacity, not speed)", 0, 301, 1, args.hour_seconds),
+        ("m0_t101_1x60s", "configs[0] mode 0 mono, 101 taps (the reference ignores `channels`: same R,L stream)", ["long_m0_t101_60s"]),
+        ("m0_t51_1x80s", "configs[1] mode 0 stereo, 51 taps, one capture, across the counter's saturation (69.9 s)", ["long_m0_t51_80s"]),
+        ("m1_t51_1x65s", "mode 1 (1.44 Msps, decim 4), 51 taps, across saturation (58.3 s)", ["long_m1_t51_65s"]),
+        ("m2_t51_1x75s", "configs[2] mode 2 (147/800 polyphase to 44.1 kHz), 51 taps, across saturation (69.9 s)", ["long_m2_t51_75s"]),
+        ("m3_t51_1x70s", "configs[2] mode 3 (2.304 Msps, 441/2560 polyphase), 51 taps, across saturation (65.5 s)", ["long_m3_t51_70s"]),
+        ("m0_t301_1x25s", "mode 0, 301 taps, one capture", ["long_m0_t301_25s"]),
+        ("m0_t51_nopilot_60s", "mode 0, a capture without a pilot (the loop never locks)", ["hostile_m0_t51_60s_nopilot"]),
+        ("m0_t51_noise_60s", "mode 0, noise only", ["hostile_m0_t51_60s_noise"]),
+        ("m2_t51_noise_20s", "mode 2, noise only", ["hostile_m2_t51_20s_noise"]),
+        ("m0_t51_64x60s", "configs[3] the bench batch: 64 stations x 60 s", [f"bench_m0_t51_60s_station{k}" for k in range(64)]),
+        ("m0_t301_1hour", "configs[4] one 3600 s capture, 301 taps, on one GPU", ["hour_m0_t301_3600s"]),
     ]
     only = {s for s in args.only.split(",") if s}
-    for name, what, mode, taps, C, seconds in cases:
+    for name, what, fixtures in cases:
         if only and name not in only:
             continue
+        if any(f not in golden for f in fixtures):
+            print(json.dumps({"config": name, "skipped": "fixture not generated"}), flush=True)
+            continue
+        gs = [golden[f] for f in fixtures]
+        g0 = gs[0]
+        mode, taps, C, nb = g0["mode"], g0["taps"], len(gs), g0["n_blocks"]
         info = fm.mode_table(mode, taps)
-        nb = max(1, int(seconds * info.rf_fs * 2 / info.block_size))
         n_pairs = nb * info.block_size // 2
-        iq = pkg.synth.synth_iq_torch(n_pairs, C, dev, info.rf_fs, first_station=0, seed=77)
+        iq = torch.empty((C, 2 * n_pairs), dtype=torch.uint8, device=dev)
+        for c, g in enumerate(gs):
+            pkg.synth.synth_iq_exact_torch(n_pairs, 1, dev, float(info.rf_fs), first_station=g["station"], kinds=[g["kind"]], out=iq[c:c + 1])
         pcm = torch.zeros((C, nb * 2 * info.audio_per_block), dtype=torch.int16, device=dev)
         stream = torch.cuda.current_stream()
-        parity = "skipped"
         with fm.Pipeline(mode, taps, C, device=0) as pipe:
             warm = max(1, min(nb, int(1.0 * info.rf_fs * 2 / info.block_size)))   # about a second of signal
             for _ in range(2):                             # warm-up on a prefix
@@ -82,19 +85,17 @@ def main():
             kern = pipe.last_timing()
             launches = pipe.kernel_launches - l0
             st = pipe.pll_state(0)
-        if port is not None:
-            chk = min(nb, 48 if mode < 2 else 2)
-            host_iq = iq[0, :chk * info.block_size].cpu().numpy()
-            ref, _ = port.chain(mode, taps).run(host_iq)
-            got = pcm[0, :chk * 2 * info.audio_per_block].cpu().numpy()
-            parity = "bit-identical" if np.array_equal(got, ref) else f"MISMATCH ({int((got != ref).sum())} samples)"
+        same = 0
+        for c, g in enumerate(gs):
+            same += hashlib.sha256(pcm[c].cpu().numpy().tobytes()).hexdigest() == g["pcm_sha256"]
         n_if = nb * info.if_per_block
         msps = C * n_pairs / (ms * 1e-3) / 1e6
         print(json.dumps({
             "config": name, "what": what, "mode": mode, "taps": taps, "captures": C, "seconds_per_capture": nb * info.block_size / 2 / info.rf_fs,
             "iq_msps": msps, "real_time_factor": msps * 1e6 / info.rf_fs, "real_time_factor_per_capture": msps * 1e6 / info.rf_fs / C,
             "ms": ms, "kernels_ms": kern, "pll_ns_per_if_sample_per_chain": kern["pll_ms"] * 1e6 / n_if,
-            "gpu_launches": launches, "trigOffset_end": float(st[5]), "parity_first_blocks": parity,
+            "gpu_launches": launches, "trigOffset_end": float(st[5]),
+            "parity_whole_run": f"{same}/{C} captures bit-identical to the reference PCM (sha256 over {nb * 2 * info.audio_per_block} int16 each)",
         }), flush=True)
         del iq, pcm
         torch.cuda.empty_cache()
