@@ -16,6 +16,7 @@
 // FIR arithmetic is acc = fadd(acc, fmul(c[k], x)) from +0 with k ascending --
 // the reference's exact sequence -- so one MAC costs an FMUL and an FADD: the
 // attainable ceiling of these kernels is half the FFMA peak by construction.
+#include <cstddef>
 #include <mutex>
 
 #include "fmrx_internal.h"
@@ -386,28 +387,34 @@ constexpr int PLL_GROUP = 1024;          // steps between checkpoints / barriers
 constexpr int PLL_RING = 4 * PLL_GROUP;  // per-sample input ring: 4 groups
 constexpr int kPllSpareSms = 32;         // SMs that must stay free for the FIR kernels before PLL CTAs claim whole SMs
 constexpr int PLL_TABLES = 128;          // candidate tables in flight (a ring over the steps)
-constexpr int PLL_PH_RING = 256;         // predicted-phaseEst records in flight
+constexpr int PLL_PH_RING = 512;         // predicted-phaseEst records in flight
+constexpr int PLL_TABLES1 = 256;         // one-hypothesis rows in flight (16 bytes each: the same shared memory as the tables)
+constexpr int PLL_BATCH1 = 32;           // ... steps per pass of a candidate warp there: one per lane
+constexpr int PLL_LEAD1 = 256;           // ... and how far its predictor may run ahead of warp 0
+constexpr int PLL_EXACT_MAX1 = 16;       // exact blocks after which a one-hypothesis group is finished without tables
 constexpr int PLL_HEAD = 48;             // steps of the NEXT group the predictor and the candidate warps do at the end of a group,
                                          // so that warp 0 finds its first tables waiting (multiple of 16)
 constexpr int PLL_PRED_LEAD = 128;       // the predictor stays at most this far ahead of warp 0
 constexpr int PLL_SPIN_LIMIT = 1 << 16;  // bounded polling (~1 ms): a bug must not hang the GPU
 static_assert(PLL_TABLES % 16 == 0 && PLL_PH_RING % PLL_BATCH == 0, "no ring wraps inside a block of 16 steps or a batch of candidates");
 static_assert(PLL_PRED_LEAD + PLL_TABLES <= PLL_PH_RING, "a record outlives every candidate that may still need it");
+static_assert(PLL_LEAD1 + PLL_TABLES1 <= PLL_PH_RING && PLL_TABLES1 % PLL_BATCH1 == 0 && PLL_TABLES1 * 16 == PLL_TABLES * 32, "one-hypothesis rings");
 constexpr int PLL_ABANDONED = -1;        // progress value: warp 0 gave the group up
 constexpr int PLL_EXACT_MAX = PLL_GROUP / 128;  // exact blocks (an eighth of the group) after which a speculated group is given up
-constexpr int PLL_BACKOFF_MAX = 8;       // groups run unspeculated between retries after repeated failures
+constexpr int PLL_BACKOFF_MAX = 64;      // groups between retries of the three-hypothesis tables after repeated failures
+                                         // (they run on the one-hypothesis scheme meanwhile)
 
 struct __align__(16) PllIn {             // off-chain inputs of one sample
     float x;
-    int turn_hi;                         // high word of 2.0 (x < 0: half a turn) or 0.0
-    double xd;                           // (double)x
+    float c3;                            // three-hypothesis predictor: pi*(x < 0) - (w*trigOffset before this step mod 2 pi); its errorD is wrap(c3 - phaseEst)
     double inv_x;                        // 1/(double)x, IEEE divide
     double v;                            // w * trigOffset after this step (:166-167)
     int vi;                              // rint(v/ulp) for the binade the slot was prepared in ...
     float vr;                            // ... and fl32(v/ulp - vi), |vr| <= 0.5
-    float c;                             // pi*(x < 0) - (w*trigOffset before this step mod 2 pi): the predictor's errorD is wrap(c - phaseEst)
-    int pad;
+    pllcore::OneHypIn h1;                // one-hypothesis predictor: P, r, B, c (fmrx_pll_core.h), one LDS.128
 };
+static_assert(sizeof(PllIn) == 48 && offsetof(PllIn, c3) == 4 && offsetof(PllIn, vi) == 24 && offsetof(PllIn, h1) == 32, "k_pll addresses these fields by offset");
+__device__ __forceinline__ double pll_turn(float x) { return x < 0.0f ? 2.0 : 0.0; }   // half a turn, in quadrants (-0.0f: none, as atan2 has it)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void st_v4(void *p, int a, int b, int c, int d)
@@ -513,9 +520,9 @@ __device__ __noinline__ bool pll_block_exact(TableRun &r, int u0, int nsteps, co
         const PllIn i = r.ring[u & (PLL_RING - 1)];
         StepIn in;
         in.x = i.x;
-        in.xd = i.xd;
+        in.xd = (double)i.x;
         in.inv_x = i.inv_x;
-        in.turn = i2d(i.turn_hi, 0);
+        in.turn = pll_turn(i.x);
         in.v = i.v;
         if (!chain_step_fast(c, r.k, K, in))
             chain_step_generic(c, r.k, i.x);
@@ -529,9 +536,9 @@ __device__ __noinline__ bool pll_block_exact(TableRun &r, int u0, int nsteps, co
         return false;
     // Kp*errorD, Ki*errorD of the sample after the block, from the now known trigArg
     const PllIn nx = r.ring[(u0 + nsteps) & (PLL_RING - 1)];
-    const Feedback f = make_feedback(K, c.tad, i2d(nx.turn_hi, 0), nx.inv_x, nullptr, nullptr);
+    const Feedback f = make_feedback(K, c.tad, pll_turn(nx.x), nx.inv_x, nullptr, nullptr);
     bool ok = true;
-    float ed = error_from_feedback(f, nx.x, nx.xd, ok);
+    float ed = error_from_feedback(f, nx.x, (double)nx.x, ok);
     if (!ok) {           // the shortcut's guard: the reference's own atan2 of its own float products
         float fi, fq;
         chain_feedback(c, fi, fq);
@@ -551,13 +558,13 @@ __device__ __noinline__ bool pll_block_exact(TableRun &r, int u0, int nsteps, co
 // (irregular trigOffset, trigArg beyond the exact-reduction range) -- is stepped again
 // with the checked step, which falls back to the reference's statements one by one.
 // Parks the float trigArg of every step.
-__device__ __noinline__ void pll_group_checked(pllcore::Chain &chain, const pllcore::Consts k, const PllIn *ring, int base, int cnt,
-                                               bool regular, unsigned sg_base)
+__device__ __noinline__ void pll_group_checked(pllcore::Chain &chain, const pllcore::Consts k, const PllIn *ring, int base, int t_begin, int cnt,
+                                               bool regular, unsigned sg_base, bool park_ph)
 {
     using namespace pllcore;
     const TrigK K = trig_constants();
     Chain ch = chain;
-    for (int tb = 0; tb < cnt; tb += 16) {
+    for (int tb = t_begin; tb < cnt; tb += 16) {
         const int nb = min(16, cnt - tb);
         const Chain ckb = ch;
         bool okb = regular && ch.binade != FMRX_DISARMED;
@@ -566,24 +573,184 @@ __device__ __noinline__ void pll_group_checked(pllcore::Chain &chain, const pllc
                 const PllIn i = ring[(base + t) & (PLL_RING - 1)];
                 StepIn in;
                 in.x = i.x;
-                in.xd = i.xd;
+                in.xd = (double)i.x;
                 in.inv_x = i.inv_x;
-                in.turn = i2d(i.turn_hi, 0);
+                in.turn = pll_turn(i.x);
                 in.v = i.v;
                 okb &= chain_step_spec(ch, k, K, in);
                 // (no "memory" clobber: nothing here reads s_g, and the next sample's inputs may be loaded early)
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)t), "r"(__float_as_int(__double2float_rn(ch.tad))));
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)t),
+                             "r"(park_ph ? __float_as_int(ch.ph) : __float_as_int(__double2float_rn(ch.tad))));
             }
         }
         if (!okb) {
             ch = ckb;
             for (int t = tb; t < tb + nb; t++) {
                 const float ta = chain_step(ch, k, K, ring[(base + t) & (PLL_RING - 1)].x, nullptr);
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)t), "r"(__float_as_int(ta)) : "memory");
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)t), "r"(park_ph ? __float_as_int(ch.ph) : __float_as_int(ta)) : "memory");
             }
         }
     }
     chain = ch;
+}
+
+// ---- the one-hypothesis steps of one group (warp 0) -----------------------------------
+//
+// fmrx_pll_core.h ("the one-hypothesis scheme") has the idea; here warp 0's part.  A row of step u holds
+// Kp*errorD, Ki*errorD of sample u -- the EXACT phase detector, evaluated by a candidate lane for the trigArg
+// the reference forms (:167) from the predictor's phaseEst of step u - 1 -- and the predictor's phaseEst of
+// step u.  Warp 0 runs the loop filter (:163-164: three dependent float additions per step) and XORs its
+// phaseEst with the predicted one.  Induction over a block of 16: the block starts from a phaseEst equal to
+// the prediction (checked), so row u0 was computed for the true trigArg, so phaseEst(u0) is the reference's;
+// if that equals the prediction again, row u0 + 1 was computed for the true trigArg, and so on.  A block with
+// any mismatch (or a candidate's guard, or a row that is not this step's) is stepped again the exact way from
+// its checkpoint, after which the comparison simply goes on: the predictor's trajectory and the exact one
+// usually re-merge within a block or two (phaseEst's coarse rounding forgets small differences).
+// The chain is three times faster than the predictor that feeds it, so unlike the table steps it WAITS for
+// its rows.  Parks the bits of phaseEst per step; the I/O warps turn them into trigArg (:167) in parallel.
+struct __align__(16) PllRow1 {
+    float kpe, kie;                  // Kp*errorD, Ki*errorD of this step's sample
+    int ph_bits;                     // the predictor's phaseEst after this step
+    int stamp;                       // step + 1; -(step + 1) if a guard of the candidate failed (present, not usable)
+};
+static_assert(sizeof(PllRow1) == 16, "one LDS.128 per step");
+
+struct OneRun {
+    float integ, ph;                 // in/out: loop filter state
+    int base, cnt;
+    unsigned tab_base, sg_base, prog_addr;
+    const PllIn *ring;
+    pllcore::Consts k;
+    float toff_base;                 // trigOffset before the group
+    double tad0;                     // trigArg before the group (exact)
+    int n_exact;                     // out: blocks stepped the exact way
+    int done;                        // out: steps completed here (< cnt: the caller finishes the group without tables)
+    int timed_out;                   // out: a row never came
+};
+
+// the chain state after `steps_done` steps of the group, from the loop filter state and the trigArg it implies
+__device__ __forceinline__ void onehyp_chain_at(pllcore::Chain &c, float integ, float ph, float toff, double tad)
+{
+    using namespace pllcore;
+    c.integ = integ;
+    c.ph = ph;
+    c.toff = toff;
+    c.tad = tad;
+    c.cr = c.sr = c.r = c.nd = c.ulp = c.inv_ulp = 0.0;
+    c.cf = c.sf = 0.0f;
+    c.binade = FMRX_DISARMED;
+    if (fabs(tad) <= (double)FMRX_FAST_TRIG_MAX) {
+        chain_refresh(c);
+    } else {                             // beyond the exact-reduction range: the library functions (:168-169)
+        c.fi = p_d2f(cos(tad));
+        c.fq = p_d2f(sin(tad));
+    }
+}
+
+__device__ __noinline__ void pll_block_exact1(OneRun &r, int u0, int nsteps, float &integ, float &ph)
+{
+    using namespace pllcore;
+    const TrigK K = trig_constants();
+    Chain c;
+    const double tad = u0 == r.base ? r.tad0 : onehyp_trigarg(r.ring[(u0 - 1) & (PLL_RING - 1)].v, ph);
+    onehyp_chain_at(c, integ, ph, fminf(r.toff_base + (float)(u0 - r.base), 16777216.0f), tad);
+    for (int j = 0; j < nsteps; j++) {
+        const PllIn i = r.ring[(u0 + j) & (PLL_RING - 1)];
+        StepIn in;
+        in.x = i.x;
+        in.xd = (double)i.x;
+        in.inv_x = i.inv_x;
+        in.turn = pll_turn(i.x);
+        in.v = i.v;
+        if (c.binade == FMRX_DISARMED || !chain_step_fast(c, r.k, K, in))
+            chain_step_generic(c, r.k, i.x);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(r.sg_base + 4u * (unsigned)(u0 + j - r.base)), "r"(__float_as_int(c.ph)) : "memory");
+    }
+    integ = c.integ;
+    ph = c.ph;
+}
+
+__device__ __noinline__ void pll_onehyp_group(OneRun &r, const int lane)
+{
+    using namespace pllcore;
+    float integ = r.integ, ph = r.ph;
+    const int base = r.base, cnt = r.cnt;
+    const unsigned tab_base = r.tab_base, sg_base = r.sg_base, prog_addr = r.prog_addr;
+    int last_pred = __float_as_int(ph);          // the predictor starts the group from this very phaseEst
+    int n_exact = 0, t = 0;
+    bool timed_out = false;
+    auto load_row = [&](unsigned addr) {
+        int4 v;
+        asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+        return v;
+    };
+    for (; t < cnt; t += 16) {
+        const int u0 = base + t, nb = min(16, cnt - t);
+        // wait (bounded) for the block's last row: the candidate warps store a batch of 32 rows with one
+        // instruction, so the block's other rows are there too (each row's own stamp is checked anyway)
+        {
+            const unsigned a_last = tab_base + (unsigned)((u0 + nb - 1) & (PLL_TABLES1 - 1)) * 16u + 12u;
+            int z, spin = 0;
+            do {
+                asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(z) : "r"(a_last) : "memory");
+            } while (z != u0 + nb && z != -(u0 + nb) && ++spin < PLL_SPIN_LIMIT);
+            if (spin >= PLL_SPIN_LIMIT) {
+                timed_out = true;
+                break;
+            }
+        }
+        const float integ0 = integ, ph0 = ph;
+        int bad = __float_as_int(ph) ^ last_pred;
+        const unsigned row0 = tab_base + (unsigned)(u0 & (PLL_TABLES1 - 1)) * 16u;     // rows do not wrap inside a block of 16
+        if (nb == 16) {
+            int park[16];
+#pragma unroll
+            for (int h = 0; h < 16; h += 8) {
+                int4 rw[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    rw[j] = load_row(row0 + (unsigned)(h + j) * 16u);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    integ = p_faddf(integ, __int_as_float(rw[j].y));                               // :163
+                    ph = p_faddf(ph, p_faddf(__int_as_float(rw[j].x), integ));                     // :164
+                    bad |= (__float_as_int(ph) ^ rw[j].z) | (rw[j].w ^ (u0 + h + j + 1));
+                    park[h + j] = __float_as_int(ph);
+                }
+                last_pred = rw[7].z;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(park[j]), "r"(park[j + 1]),
+                             "r"(park[j + 2]), "r"(park[j + 3])
+                             : "memory");
+        } else {
+            for (int j = 0; j < nb; j++) {
+                const int4 rw = load_row(row0 + (unsigned)j * 16u);
+                integ = p_faddf(integ, __int_as_float(rw.y));
+                ph = p_faddf(ph, p_faddf(__int_as_float(rw.x), integ));
+                bad |= (__float_as_int(ph) ^ rw.z) | (rw.w ^ (u0 + j + 1));
+                last_pred = rw.z;
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(__float_as_int(ph)) : "memory");
+            }
+        }
+        if (bad) {
+            integ = integ0;
+            ph = ph0;
+            pll_block_exact1(r, u0, nb, integ, ph);
+            if (++n_exact > PLL_EXACT_MAX1) {        // the predictor has lost the trajectory for good: no more waiting for its rows
+                t += nb;
+                break;
+            }
+        }
+        asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(prog_addr), "r"(u0 + nb) : "memory");
+    }
+    r.integ = integ;
+    r.ph = ph;
+    r.n_exact = n_exact;
+    r.done = min(t, cnt);
+    r.timed_out = timed_out;
+    (void)lane;
 }
 
 // A candidate table: what the next sample's phase detector gives for the three float-grid
@@ -790,16 +957,12 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(gis[j]), "r"(gis[j + 1]),
                          "r"(gis[j + 2]), "r"(gis[j + 3])
                          : "memory");
-        // The 16 stamps once more, lane j that of row j: a row is read as two halves (stamp half first),
-        // so a row REPLACED between the two loads -- by a candidate warp that fell a whole ring behind
-        // and stores the table of step u - PLL_TABLES late -- would pass the first check with the other
-        // step's data.  Any store to a row changes its stamp (one stamp per step block and pi), so the
-        // stamp still being there now means both halves were this block's.
-        {
-            int z;
-            asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(z) : "r"(tab_a0 + (unsigned)(lane & 15) * (unsigned)sizeof(PllRow) + 28u) : "memory");
-            bad |= __any_sync(0xffffffffu, z != stamp);
-        }
+        // (A row is read as two halves, stamp half first, so a row REPLACED between the two loads would pass the
+        // check with another step's data.  The only writer that could do that is a candidate warp a whole ring
+        // behind, storing the table of step u - PLL_TABLES late; it looks at warp 0's progress immediately before
+        // its store and skips it if warp 0 has left its batch behind, and warp 0 cannot cover the 120 steps from
+        // there to this row in the few cycles between that look and the store.  Reading the 16 stamps once more
+        // here instead cost 7 cycles per step: the dependent LDS + vote sits on the block's critical path.)
         if (!settle(u0, 16, integ0, ph0, gi0) || n_exact > PLL_EXACT_MAX) {
             fatal = true;            // (more exact blocks than a group without tables costs: give the group up)
             break;
@@ -824,12 +987,6 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
             gi = vg.x + kbase + __float_as_int(p_faddf(p_faddf(__int_as_float(tb), __int_as_float(vg.y)), 12582912.0f));
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(tb) : "memory");
         }
-        {   // the stamps once more (see the full blocks)
-            int z = pll_stamp(u0, kbase);
-            if (lane < nb)
-                asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(z) : "r"(tab_base + (unsigned)((u0 + lane) & (PLL_TABLES - 1)) * (unsigned)sizeof(PllRow) + 28u) : "memory");
-            bad |= __any_sync(0xffffffffu, z != pll_stamp(u0, kbase));
-        }
         fatal = !settle(u0, nb, integ0, ph0, gi0);
     }
     r.fatal = fatal;
@@ -847,18 +1004,22 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     extern __shared__ __align__(16) unsigned char pll_dyn_smem[];
     PllIn *s_in = reinterpret_cast<PllIn *>(pll_dyn_smem);      // [PLL_RING]
     __shared__ __align__(16) int2 s_ph[PLL_PH_RING];  // {predicted phaseEst, step + 1}, written by the predictor warp
-    __shared__ float s_hdr[2];                        // integrator, phaseEst at the start of the group (warp 0 -> predictor)
+    __shared__ float s_hdr[3];                        // integrator, phaseEst at the start of the group (warp 0 -> predictor, I/O) and the
+                                                      // mean slope of phaseEst over the group before (I/O: where phaseEst is heading)
+    __shared__ double s_hdr_tad;                      // trigArg before the group (exact)
     __shared__ int s_kbase;                           // rint(phaseEst/ulp) at the start of the group, less the bits of 1.5 * 2^23
     __shared__ int s_kb_blk[2][PLL_GROUP / 16];       // kbase of every block of the group whose parked values are in s_g[.]
     __shared__ int s_prog;                            // steps of the capture warp 0 has completed (per block of 16), or PLL_ABANDONED
-    __shared__ PllRow s_tab[PLL_TABLES];              // candidate tables, a ring over the steps
-    __shared__ __align__(16) int s_g[2][PLL_GROUP];                 // grid index of each trigArg of the group, double-buffered
+    __shared__ PllRow s_tab[PLL_TABLES];              // candidate tables, a ring over the steps (one-hypothesis groups: PLL_TABLES1 rows of 16 bytes)
+    __shared__ __align__(16) int s_g[2][PLL_GROUP];                 // what warp 0 parks per step of the group (see s_spec), double-buffered
     __shared__ double s_grid[2];                      // ulp, 1/ulp of the current group
     __shared__ double s_prep_ulp[4];                  // ulp the ring slots of each group were prepared with
     __shared__ double s_ulp_hist[2];                  // ulp the parked grid indices of a group refer to
-    __shared__ int s_spec[2];                         // 1: s_g holds grid indices, 0: float bit patterns
-    __shared__ int s_flag[4];                         // [0] group runs speculatively, [1] error, [2] the next group's slots are stale,
-                                                      // [3] the group continues the one before (its head is already done)
+    __shared__ int s_spec[2];                         // what s_g holds: 0 float trigArg, 1 the bits of t (three-hypothesis steps), 2 the bits of phaseEst
+    __shared__ int s_flag[5];                         // [0] scheme of the group: 0 none, 3 three hypotheses, 1 one hypothesis; [1] error;
+                                                      // [2] the next group's slots are stale; [3] the group continues the one before (its head
+                                                      // is already done); [4] this pass repeats the group of the pass before (its tables failed)
+    __shared__ int s_redo;                            // warp 0, at the end of a pass: do this group again (on the one-hypothesis scheme)
 
     const int c = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -882,52 +1043,58 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     const int io_id = warp >> 2;                          // 0, 1 for warps 1, 5 (2: warp 9, the predictor)
     const int cand_id = (warp >> 2) * 2 + role - 2;       // 0..5 for warps 2, 3, 6, 7, 10, 11
 
-    // I/O warp: one lane per sample, off-chain inputs of the samples of a group into the ring
-    auto prepare = [&](int base) {
+    // I/O warp: one lane per sample, off-chain inputs of the samples of a group into the ring.  The one-hypothesis
+    // inputs extrapolate phaseEst from e_ph, its value before step e_base, with e_slope per step.
+    auto prepare = [&](int base, float e_slope, float e_ph, int e_base) {
         for (int j = 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS) {
             const int u = base + j + lane;
             const float pvv = (u < n) ? p[u] : 1.0f;
+            const float pnx = (u + 1 < n) ? p[u + 1] : 1.0f;
             PllIn in;
             in.x = pvv;
-            in.turn_hi = (pvv < 0.0f) ? 0x40000000 : 0;
-            in.xd = (double)pvv;
-            in.inv_x = 1.0 / in.xd;                                      // IEEE divide
+            in.inv_x = 1.0 / (double)pvv;                                // IEEE divide
             const float toff = (float)min(t0 + u + 1, 16777216);         // exact: <= 2^24
             in.v = __dmul_rn(k.w, (double)toff);
             // v on the float grid of the current binade: integer part and remainder
             const double qv = grid_round(in.v, s_grid[1]);
             in.vi = grid_index(qv);
             in.vr = __double2float_rn(__fma_rn(in.v, s_grid[1], -p_add(qv, -FMRX_RINT_MAGIC)));
-            in.c = predictor_c(k, pvv, (float)min(t0 + u, 16777216));      // trigOffset BEFORE this step
-            in.pad = 0;
+            in.c3 = predictor_c(k, pvv, (float)min(t0 + u, 16777216));      // trigOffset BEFORE this step
+            in.h1 = onehyp_inputs(in.v, e_ph, e_slope, u + 1 - e_base, pnx);
             s_in[u & (PLL_RING - 1)] = in;
         }
         if (lane == 0 && io_id == 0)
             s_prep_ulp[(base / PLL_GROUP) & 3] = s_grid[0];
     };
 
-    if (threadIdx.x < PLL_PH_RING)
-        s_ph[threadIdx.x] = make_int2(0, 0);
+    for (int i = threadIdx.x; i < PLL_PH_RING; i += PLL_THREADS)
+        s_ph[i] = make_int2(0, 0);
     for (int i = threadIdx.x; i < PLL_TABLES; i += PLL_THREADS) {
         s_tab[i].lp = PLL_ROW_INVALID;
         s_tab[i].stamp = 0;
+        s_tab[i].kie0 = 0.0f;            // (the stamp word of the one-hypothesis row in the table's first half)
     }
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         s_flag[1] = 0;
+        s_redo = 0;
+    }
     // warp 0 owns the recurrence state
     Chain ch;
     bool stale = false;              // ch's sincos leftovers lag behind ch.tad (after speculative groups)
     bool have_ed = false;            // kpe_next/kie_next below belong to the next sample
     float kpe_next = 0.0f, kie_next = 0.0f;
     bool dead = false;               // a hand-off timed out: stay on the checked path
-    int backoff = 0, skip = 0;       // after a failed group: run `skip` groups checked, then retry
+    int backoff = 0, skip = 0;       // after a failed table group: `skip` groups without the tables, then retry
+    int prev_scheme = 0;
+    float ph_hdr_prev = 0.0f;        // phaseEst at the start of the group before (lane 0 of warp 0)
     int n_groups = 0, n_redone = 0, n_exact = 0, prev_exact = 0;
     float pred_integ = 0.0f, pred_ph = 0.0f;          // the predictor's state (warp 9)
 #ifdef FMRX_PLL_PROFILE
-    long long prof_steps_cyc = 0, prof_wait = 0, prof_pre = 0;
+    long long prof_steps_cyc = 0, prof_wait = 0, prof_pre = 0, prof_one_cyc = 0;
     const long long prof_k0 = clock64();
     int prof_steps = 0, prof_n_stamp = 0, prof_n_c = 0, prof_n_fe = 0, prof_n_fm = 0;
     int prof_n_tie = 0, prof_n_range = 0, prof_n_inv = 0;
+    int prof_one_steps = 0, prof_one_groups = 0, prof_one_exact = 0, prof_one_short = 0, prof_checked = 0;
     __shared__ int s_prof[8];        // candidate warps: why a table was not emitted
     if (threadIdx.x < 8)
         s_prof[threadIdx.x] = 0;
@@ -946,35 +1113,46 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     }
     __syncthreads();
     if (role == 1 && io_id < PLL_IO_WARPS) {
-        prepare(0);
-        prepare(PLL_GROUP);
+        prepare(0, st[0], st[1], 0);
+        prepare(PLL_GROUP, st[0], st[1], 0);
     }
     __syncthreads();
 
-    for (int base = 0, g = 0; base < n; base += PLL_GROUP, g++) {
+    for (int base = 0, g = 0; base < n;) {
         const int cnt = min(PLL_GROUP, n - base);
         Chain ck;
         // ---- group header (warp 0) ----
         if (warp == 0) {
             ck = ch;
-            // The hypotheses of a step are NEIGHBOURING float-grid points of trigArg, which presumes that
-            // phaseEst moves on a grid at least as fine.  Where the reference hands the PLL if_fs*interp
-            // (modes 2/3) phaseEst cancels w*trigOffset, trigArg is a small difference of large floats and
-            // its possible values lie a whole phaseEst spacing (thousands of its own grid steps) apart:
-            // no tables there.
-            const bool spec = regular && !dead && skip == 0 && ch.binade != FMRX_DISARMED &&
-                              s_prep_ulp[g & 3] == ch.ulp && (double)fabsf(ch.ph) < ch.ulp * 16777216.0;
+            const bool again = s_redo != 0;          // (uniform: written before the barrier that ended the last pass)
+            // (disarmed: a state whose feedback pair does not belong to its trigArg -- a hand-made one -- or a
+            // trigArg of 0 or beyond 2^24: the checked step sorts that out)
+            const bool usable = regular && !dead && ch.binade != FMRX_DISARMED && fabs(ch.tad) <= (double)FMRX_FAST_TRIG_MAX;
+            // The hypotheses of a three-hypothesis step are NEIGHBOURING float-grid points of trigArg, which presumes
+            // that phaseEst moves on a grid at least as fine.  Where the reference hands the PLL if_fs*interp (modes
+            // 2/3) phaseEst cancels w*trigOffset, trigArg is a small difference of large floats and its possible values
+            // lie a whole phaseEst spacing (thousands of its own grid steps) apart: there -- and while the tables are
+            // backing off after a failure, e.g. on a loop that locks onto nothing -- the one-hypothesis scheme runs.
             // (Tables also serve the regime past trigOffset == 2^24, where trigArg freezes on two grid points
             // and the loop dithers across a float rounding boundary: tests/test_gpu_operators.py::
-            // test_pll_long_run_past_counter_saturation and the >= 70 s pipeline runs of
-            // tests/test_gpu_long_runs.py.  Round 1 kept them off there until the stale-head fix just
-            // below had been run on a GPU.)
-
+            // test_pll_long_run_past_counter_saturation and the >= 70 s pipeline runs of tests/test_gpu_long_runs.py.)
+            const bool can3 = usable && !again && skip == 0 && s_prep_ulp[g & 3] == ch.ulp &&
+                              (double)fabsf(ch.ph) < ch.ulp * 16777216.0;
+            const int scheme = can3 ? 3 : usable ? 1 : 0;
             // the group before ran on tables to its end and hardly needed the exact step: predictor and
             // candidates did our head, and the predictor carries on from its own state (otherwise it
             // restarts from the exact one: it may have drifted)
-            const bool cont = spec && have_ed && prev_exact <= 2;
-            if (!cont && base > 0) {
+            const bool cont = scheme == 3 && prev_scheme == 3 && have_ed && prev_exact <= 2;
+            if (scheme != prev_scheme || again) {
+                // the other scheme's rows (and records) share the rings: nothing of them may be taken for this group's
+                for (int i = lane; i < PLL_TABLES; i += 32) {
+                    s_tab[i].lp = PLL_ROW_INVALID;
+                    s_tab[i].stamp = 0;
+                    s_tab[i].kie0 = 0.0f;
+                }
+                for (int i = lane; i < PLL_PH_RING; i += 32)
+                    s_ph[i] = make_int2(0, 0);
+            } else if (scheme == 3 && !cont && base > 0) {
                 // ... and then the head that the group before prepared must go: its tables carry this
                 // group's stamps and its records this group's sequence numbers, but their block pi came
                 // from the OLD predictor run, while warp 0 now takes pi of the first block from the exact
@@ -989,19 +1167,30 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 }
             }
             if (lane == 0) {
-                s_flag[0] = spec;
+                s_flag[0] = scheme;
                 s_grid[0] = ch.ulp;
                 s_grid[1] = ch.inv_ulp;
-                s_flag[2] = s_prep_ulp[(g + 1) & 3] != ch.ulp;
+                s_flag[2] = ch.binade != FMRX_DISARMED && s_prep_ulp[(g + 1) & 3] != ch.ulp;
                 s_flag[3] = cont;
+                s_flag[4] = again;
                 s_kbase = __float_as_int(p_faddf(p_fmulf(ch.ph, (float)ch.inv_ulp), 12582912.0f)) - 0x4B400000 - 0x4B400000;
                 s_hdr[0] = ch.integ;
                 s_hdr[1] = ch.ph;
+                // where phaseEst is heading: its mean slope over the group before (at the start of a launch: the
+                // integrator, which is that slope on a loop at rest -- but e.g. in modes 2/3 the phase detector's
+                // output has a mean of its own, and 3000 steps ahead the difference is whole turns)
+                if (!again) {
+                    s_hdr[2] = g > 0 ? p_fmulf(p_faddf(ch.ph, -ph_hdr_prev), 1.0f / PLL_GROUP) : ch.integ;
+                    ph_hdr_prev = ch.ph;
+                }
+                s_hdr_tad = ch.tad;
                 s_prog = base;
             }
         }
         __syncthreads();
-        const bool spec = s_flag[0] != 0;
+        const int scheme = s_flag[0];
+        const bool spec = scheme == 3;
+        const bool again = s_flag[4] != 0;
         const double ulp = s_grid[0], inv_ulp = s_grid[1];
 #ifdef FMRX_PLL_PROFILE
         const long long prof_ga = clock64();
@@ -1009,15 +1198,20 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
 
         if (warp == 0) {
             // ================= the chain =================
-            n_groups++;
-            bool good = spec;
-            if (spec) {
+            if (lane == 0)
+                s_redo = 0;          // (every warp read it after the barrier that ended the last pass)
+            if (!again)
+                n_groups++;
+            bool good = scheme != 0;
+            bool redo = false;
+            int parked = 0;          // what s_g holds at the end (s_spec)
+            if (scheme == 3) {
                 float integ = ch.integ, ph = ch.ph;
                 float kpe = kpe_next, kie = kie_next;        // Kp*errorD, Ki*errorD of the sample about to run
                 if (!have_ed) {      // first group, or after a checked group: from the known trigArg
                     const PllIn i0 = s_in[base & (PLL_RING - 1)];
-                    const Feedback f0 = make_feedback(K, ch.tad, i2d(i0.turn_hi, 0), i0.inv_x, nullptr, nullptr);
-                    const float ed = error_from_feedback(f0, i0.x, i0.xd, good);
+                    const Feedback f0 = make_feedback(K, ch.tad, pll_turn(i0.x), i0.inv_x, nullptr, nullptr);
+                    const float ed = error_from_feedback(f0, i0.x, (double)i0.x, good);
                     kpe = p_fmulf(k.kp, ed);
                     kie = p_fmulf(k.ki, ed);
                 }
@@ -1069,7 +1263,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 r.kbase = cu_base;
                 r.base = base;
                 r.cnt = cnt;
-                r.in_base = smem_u32(&s_in[0]) + 32u;                            // offset of {vi, vr} in a slot
+                r.in_base = smem_u32(&s_in[0]) + (unsigned)offsetof(PllIn, vi);   // {vi, vr} of a slot
                 r.tab_base = smem_u32(&s_tab[0]);
                 r.sg_base = smem_u32(&s_g[g & 1][0]);
                 r.prog_addr = smem_u32(&s_prog);
@@ -1118,37 +1312,109 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     kpe_next = r.kpe;
                     kie_next = r.kie;
                     backoff = 0;
-                }
-            }
-            if (!good) {
-                if (spec) {
-                    // the predictor and the candidate warps stop working on this group
+                    parked = 1;
+                } else {
+                    // the predictor and the candidate warps stop working on this group; it is done again, on the
+                    // one-hypothesis scheme, and the tables rest for a while
                     asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(smem_u32(&s_prog)), "r"(PLL_ABANDONED) : "memory");
                     n_redone++;
                     backoff = min(backoff ? 2 * backoff : 1, PLL_BACKOFF_MAX);
-                    skip = backoff - 1;
-                } else if (skip > 0) {
-                    skip--;
+                    skip = backoff;
+                    ch = ck;
+                    have_ed = false;
+                    redo = !dead;
+                    if (!redo) {         // a hand-off timed out: no second pass, the group goes without tables right here
+                        if (stale) {
+                            chain_refresh(ch);
+                            stale = false;
+                        }
+                        pll_group_checked(ch, k, s_in, base, 0, cnt, regular, smem_u32(&s_g[g & 1][0]), false);
+                    }
                 }
-                ch = ck;
+            } else if (scheme == 1) {
+                if (skip > 0 && !again)
+                    skip--;
+                OneRun r;
+                r.integ = ch.integ;
+                r.ph = ch.ph;
+                r.base = base;
+                r.cnt = cnt;
+                r.tab_base = smem_u32(&s_tab[0]);
+                r.sg_base = smem_u32(&s_g[g & 1][0]);
+                r.prog_addr = smem_u32(&s_prog);
+                r.ring = s_in;
+                r.k = k;
+                r.toff_base = ch.toff;
+                r.tad0 = ch.tad;
+                r.n_exact = 0;
+                r.done = 0;
+                r.timed_out = 0;
+                __syncwarp();
+#ifdef FMRX_PLL_PROFILE
+                const long long prof_c0 = clock64();
+#endif
+                pll_onehyp_group(r, lane);
+#ifdef FMRX_PLL_PROFILE
+                prof_one_cyc += clock64() - prof_c0;
+                prof_one_steps += r.done;
+                prof_one_groups++;
+                prof_one_exact += r.n_exact;
+                prof_one_short += r.done < cnt;
+#endif
+                n_exact += r.n_exact;
+                if (r.timed_out) {
+                    dead = true;
+                    if (lane == 0)
+                        s_flag[1] = 1;
+                }
+                // the state after r.done steps; what is left of the group (the predictor lost the trajectory) goes without tables
+                const int last = base + r.done - 1;
+                const double tad = r.done ? onehyp_trigarg(s_in[last & (PLL_RING - 1)].v, r.ph) : ch.tad;
+                if (r.done < cnt) {
+                    asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(smem_u32(&s_prog)), "r"(PLL_ABANDONED) : "memory");
+                    onehyp_chain_at(ch, r.integ, r.ph, (float)min(t0 + base + r.done, 16777216), tad);
+                    pll_group_checked(ch, k, s_in, base, r.done, cnt, regular, smem_u32(&s_g[g & 1][0]), true);
+                    stale = false;
+                } else {
+                    ch.integ = r.integ;
+                    ch.ph = r.ph;
+                    ch.toff = (float)min(t0 + base + cnt, 16777216);
+                    ch.tad = tad;
+                    stale = true;
+                    if (fabs(tad) <= (double)FMRX_FAST_TRIG_MAX)
+                        chain_arm(ch);           // the binade may have changed (the header wants ulp and binade)
+                    else
+                        onehyp_chain_at(ch, r.integ, r.ph, ch.toff, tad), stale = false;
+                }
+                have_ed = false;
+                parked = 2;
+            } else {
+                if (skip > 0)
+                    skip--;
                 if (stale) {         // bring the sincos leftovers up to date with ch.tad
                     chain_refresh(ch);
                     stale = false;
                 }
                 // the group without tables (a separately compiled function, like the table steps)
-                pll_group_checked(ch, k, s_in, base, cnt, regular, smem_u32(&s_g[g & 1][0]));
+#ifdef FMRX_PLL_PROFILE
+                prof_checked++;
+#endif
+                pll_group_checked(ch, k, s_in, base, 0, cnt, regular, smem_u32(&s_g[g & 1][0]), false);
                 have_ed = false;
+                parked = 0;
             }
+            prev_scheme = redo ? 0 : scheme;
             if (lane == 0) {
-                s_spec[g & 1] = good ? 1 : 0;
+                s_spec[g & 1] = parked;
                 s_ulp_hist[g & 1] = ulp;
+                s_redo = redo;
             }
         } else if (role >= 2) {
             // ================= candidate tables =================
-            // A warp evaluates eight consecutive steps at once, one per quad of lanes: lane 4*s + j
-            // takes step base + 8*cand_id + s (mod 8*PLL_CAND_WARPS) and the grid point G_c - 1 + j
-            // around the predictor's trigArg of that step (j = 3 is idle work: SIMT).
-            if (spec) {
+            if (scheme == 3) {
+                // A warp evaluates eight consecutive steps at once, one per quad of lanes: lane 4*s + j
+                // takes step base + 8*cand_id + s (mod 8*PLL_CAND_WARPS) and the grid point G_c - 1 + j
+                // around the predictor's trigArg of that step (j = 3 is idle work: SIMT).
                 const int sq = lane >> 2, jq = lane & 3;
                 const unsigned prog_a = smem_u32(&s_prog);
                 auto progress = [&]() {
@@ -1203,14 +1469,14 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const int gc = grid_index(grid_round(p_add(v, (double)__int_as_float(pr.x)), inv_ulp));
                     const int gl = gc - 1 + jq;
                     const double tad = p_mul((double)gl, ulp);                        // exact
-                    const Feedback f = make_feedback(K, tad, i2d(nx.turn_hi, 0), nx.inv_x, nullptr, nullptr);
+                    const Feedback f = make_feedback(K, tad, pll_turn(nx.x), nx.inv_x, nullptr, nullptr);
                     // the float grid of the binade is only right strictly inside it
                     const int ag = gl < 0 ? -gl : gl;
                     bool ok = have && ag > (1 << 23) && ag < (1 << 24);
 #ifdef FMRX_PLL_PROFILE
                     const bool prof_ok_b = ok;
 #endif
-                    const float ed = error_from_feedback(f, nx.x, nx.xd, ok);         // :159-161 of sample u+1
+                    const float ed = error_from_feedback(f, nx.x, (double)nx.x, ok);  // :159-161 of sample u+1
                     // the table is good if the guards of its three grid points held
                     const int n1 = gc - (vi + kb) - 0x4B400000;                       // G_c - (vi + pi): small
 #ifdef FMRX_PLL_PROFILE
@@ -1249,15 +1515,70 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                                      : "memory");
                     }
                 }
+            } else if (scheme == 1) {
+                // One-hypothesis rows, one step per lane: the exact phase detector of sample u for the trigArg the
+                // reference forms (:167) from the predictor's phaseEst of step u - 1 (the group's first step: from the
+                // exact trigArg in the header).  Batch q of 32 steps belongs to warp q mod PLL_CAND_WARPS.
+                const unsigned prog_a = smem_u32(&s_prog);
+                auto progress = [&]() {
+                    int v;
+                    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(prog_a) : "memory");
+                    return v;
+                };
+                const int end = base + cnt;
+                for (int ub = base + cand_id * PLL_BATCH1; ub < end; ub += PLL_BATCH1 * PLL_CAND_WARPS) {
+                    const bool live = ub + lane < end;
+                    const int u = live ? ub + lane : end - 1;
+                    const int last = min(ub + PLL_BATCH1 - 1, end - 1);
+                    int prog = 0, spin = 0;
+                    for (;; spin++) {
+                        const int seq = ld_v2(&s_ph[last & (PLL_PH_RING - 1)]).y;
+                        if (seq == last + 1 || spin >= PLL_SPIN_LIMIT)
+                            break;
+                        if ((spin & 7) == 7 && (prog = progress()) == PLL_ABANDONED)
+                            break;
+                    }
+                    if (prog == PLL_ABANDONED)
+                        break;
+                    if (spin >= PLL_SPIN_LIMIT) {
+                        s_flag[1] = 1;
+                        break;
+                    }
+                    const int2 cur = ld_v2(&s_ph[u & (PLL_PH_RING - 1)]);
+                    bool ok = cur.y == u + 1;
+                    double tad = s_hdr_tad;
+                    if (u != base) {
+                        const int2 prv = ld_v2(&s_ph[(u - 1) & (PLL_PH_RING - 1)]);
+                        ok = ok && prv.y == u;
+                        tad = onehyp_trigarg(s_in[(u - 1) & (PLL_RING - 1)].v, __int_as_float(prv.x));
+                    }
+                    const float x = s_in[u & (PLL_RING - 1)].x;
+                    const double inv_x = s_in[u & (PLL_RING - 1)].inv_x;
+                    ok = ok && fabs(tad) <= (double)FMRX_FAST_TRIG_MAX;
+                    const Feedback f = make_feedback(K, ok ? tad : 0.0, pll_turn(x), inv_x, nullptr, nullptr);
+                    const float ed = error_from_feedback(f, x, (double)x, ok);        // :159-161 of sample u
+                    // the rows still hold steps u - PLL_TABLES1: wait until warp 0 is past them
+                    for (spin = 0; (prog = progress()) != PLL_ABANDONED && prog - (ub + PLL_BATCH1 - PLL_TABLES1) < 0 && spin < PLL_SPIN_LIMIT; spin++)
+                        ;
+                    if (prog == PLL_ABANDONED)
+                        break;
+                    if (spin >= PLL_SPIN_LIMIT) {
+                        s_flag[1] = 1;
+                        break;
+                    }
+                    if (live)
+                        st_v4(reinterpret_cast<PllRow1 *>(&s_tab[0]) + (u & (PLL_TABLES1 - 1)), __float_as_int(p_fmulf(k.kp, ed)),
+                              __float_as_int(p_fmulf(k.ki, ed)), cur.x, ok ? u + 1 : -(u + 1));
+                }
             }
         } else if (warp == PLL_PRED_WARP) {
             // ================= the run-ahead predictor =================
-            // The same recurrence with the phase detector replaced by what it computes up to
-            // rounding (fmrx_pll_core.h, predictor_step): nine dependent float operations per
-            // step, so it runs about twice as fast as warp 0 can consume tables, and its phaseEst
-            // stays within a grid step or two of the exact one for the whole group (it restarts
-            // from the exact state at every group).  It is only ever used to CENTRE the tables.
-            if (spec) {
+            if (scheme == 3) {
+                // The same recurrence with the phase detector replaced by what it computes up to
+                // rounding (fmrx_pll_core.h, predictor_step): nine dependent float operations per
+                // step, so it runs about twice as fast as warp 0 can consume tables, and its phaseEst
+                // stays within a grid step or two of the exact one for the whole group (it restarts
+                // from the exact state at every group).  It is only ever used to CENTRE the tables.
                 // a group that continues the one before finds its head done and the predictor's state
                 // where that left it (it needs no restart: tests/test_pll_model.py runs it for 20 s)
                 const bool cont = s_flag[3] != 0;
@@ -1268,7 +1589,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 float integ = pred_integ, ph = pred_ph;
                 const unsigned prog_a = smem_u32(&s_prog);
                 const unsigned ph_a = smem_u32(&s_ph[0]);
-                const unsigned c_a = smem_u32(&s_in[0]) + 40u;                   // offset of c in a slot
+                const unsigned c_a = smem_u32(&s_in[0]) + (unsigned)offsetof(PllIn, c3);
                 int prog = base;
                 const int t_end = cnt + (base + cnt + PLL_HEAD <= n ? PLL_HEAD : 0);
                 for (int t = cont ? PLL_HEAD : 0; t < t_end; t += 16) {
@@ -1296,32 +1617,113 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 }
                 pred_integ = integ;
                 pred_ph = ph;
+            } else if (scheme == 1) {
+                // The recurrence in the reference's own operation order with the phase detector replaced by
+                // wrap(pi*(x < 0) - trigArg) in float (fmrx_pll_core.h, onehyp_predictor_step): FMUL + 8 dependent
+                // FADD per step.  Restarted from the exact state at every group; its phaseEst of every step is what
+                // the candidate lanes evaluate the exact phase detector for and what warp 0 compares its own with.
+                float integ = s_hdr[0], ph = s_hdr[1];
+                float ang = onehyp_first_angle(s_in[base & (PLL_RING - 1)].x, s_hdr_tad);
+                int careful = 0;             // blocks still to run with the angle reduction on the chain
+                const unsigned prog_a = smem_u32(&s_prog);
+                const unsigned ph_a = smem_u32(&s_ph[0]);
+                const unsigned h_a = smem_u32(&s_in[0]) + (unsigned)offsetof(PllIn, h1);
+                int prog = base;
+                for (int t = 0; t < cnt; t += 8) {
+                    const int u0 = base + t;
+                    int spin = 0;                // stay within PLL_LEAD1 of warp 0
+                    do {
+                        asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(prog) : "r"(prog_a) : "memory");
+                    } while (prog != PLL_ABANDONED && u0 - prog > PLL_LEAD1 - 8 && ++spin < PLL_SPIN_LIMIT);
+                    if (prog == PLL_ABANDONED || spin >= PLL_SPIN_LIMIT)
+                        break;
+                    const unsigned h_a0 = h_a + (unsigned)(u0 & (PLL_RING - 1)) * (unsigned)sizeof(PllIn);
+                    const unsigned ph_a0 = ph_a + (unsigned)(u0 & (PLL_PH_RING - 1)) * 8u;
+                    OneHypIn hs[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(hs[j].P), "=f"(hs[j].r), "=f"(hs[j].B), "=f"(hs[j].c)
+                                     : "r"(h_a0 + (unsigned)j * (unsigned)sizeof(PllIn)));
+                    // eight steps without the angle reduction; if an angle left [-pi, pi] (P lost track of phaseEst by
+                    // whole turns, or a loop far from lock), the eight again with it -- and straight away for the next
+                    // blocks, trying the short step again every sixteenth block.  (Steps past the end of a short last
+                    // group are never used.)
+                    const float ang0 = ang, integ0 = integ, ph0 = ph;
+                    float phs[8];
+                    bool reduce = careful > 0;
+                    if (!reduce) {
+                        float amax = fabsf(ang);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            ang = onehyp_predictor_step(k, hs[j], ang, integ, ph);
+                            phs[j] = ph;
+                            if (j < 7)
+                                amax = fmaxf(amax, fabsf(ang));
+                        }
+                        reduce = !(amax <= FMRX_ONEHYP_PI);
+                        if (reduce)
+                            careful = 16;
+                    } else {
+                        careful--;
+                    }
+                    if (reduce) {
+                        ang = ang0;
+                        integ = integ0;
+                        ph = ph0;
+                        if (!(fabsf(ang) <= FMRX_ONEHYP_PI))
+                            ang = p_faddf(ang, -p_fmulf(6.2831855f, p_faddf(p_faddf(p_fmulf(ang, 0.15915494f), 12582912.0f), -12582912.0f)));
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            ang = onehyp_predictor_step_reduced(k, hs[j], ang, integ, ph);
+                            phs[j] = ph;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(ph_a0 + (unsigned)j * 8u), "r"(__float_as_int(phs[j])),
+                                     "r"(u0 + j + 1)
+                                     : "memory");
+                }
             }
         } else if (role == 1 && io_id < PLL_IO_WARPS) {
             // ================= I/O =================
-            // (a binade change strands the two groups prepared ahead with the old grid: the next one
-            // is prepared again here, so that only the group running now goes without tables)
-            if (s_flag[2])
-                prepare(base + PLL_GROUP);
-            prepare(base + 2 * PLL_GROUP);
-            if (g > 0) {                     // previous group: always complete
-                const int pb = base - PLL_GROUP;
-                for (int j = lane + 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS)
-                    tr[pb + j] = s_spec[(g - 1) & 1]
-                                     ? __double2float_rn(p_mul((double)parked_index(s_g[(g - 1) & 1][j], s_in[(pb + j) & (PLL_RING - 1)], s_kb_blk[(g - 1) & 1][j >> 4]),
-                                                               s_ulp_hist[(g - 1) & 1]))
-                                     : __int_as_float(s_g[(g - 1) & 1][j]);
+            if (!again) {            // (a pass that repeats a group has nothing new to load or store)
+                // (a binade change strands the two groups prepared ahead with the old grid: the next one
+                // is prepared again here, so that only the group running now goes without tables)
+                if (s_flag[2])
+                    prepare(base + PLL_GROUP, s_hdr[2], s_hdr[1], base);
+                prepare(base + 2 * PLL_GROUP, s_hdr[2], s_hdr[1], base);
+                if (g > 0) {                     // previous group: always complete
+                    const int pb = base - PLL_GROUP, pg = (g - 1) & 1;
+                    const int kind = s_spec[pg];
+                    for (int j = lane + 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS) {
+                        const PllIn &in = s_in[(pb + j) & (PLL_RING - 1)];
+                        const int w = s_g[pg][j];
+                        tr[pb + j] = kind == 1   ? __double2float_rn(p_mul((double)parked_index(w, in, s_kb_blk[pg][j >> 4]), s_ulp_hist[pg]))
+                                     : kind == 2 ? __double2float_rn(onehyp_trigarg(in.v, __int_as_float(w)))
+                                                 : __int_as_float(w);
+                    }
+                }
             }
         }
         __syncthreads();
+        if (!s_redo) {
+            base += PLL_GROUP;
+            g++;
+        }
     }
     // the last group's trigArg
     if (warp == 1 && n > 0) {
-        const int g = (n - 1) / PLL_GROUP, pb = g * PLL_GROUP;
-        for (int j = lane; pb + j < n && j < PLL_GROUP; j += 32)
-            tr[pb + j] = s_spec[g & 1] ? __double2float_rn(p_mul((double)parked_index(s_g[g & 1][j], s_in[(pb + j) & (PLL_RING - 1)], s_kb_blk[g & 1][j >> 4]),
-                                                                 s_ulp_hist[g & 1]))
-                                       : __int_as_float(s_g[g & 1][j]);
+        const int g = (n - 1) / PLL_GROUP, pb = g * PLL_GROUP, pg = g & 1;
+        const int kind = s_spec[pg];
+        for (int j = lane; pb + j < n && j < PLL_GROUP; j += 32) {
+            const PllIn &in = s_in[(pb + j) & (PLL_RING - 1)];
+            const int w = s_g[pg][j];
+            tr[pb + j] = kind == 1   ? __double2float_rn(p_mul((double)parked_index(w, in, s_kb_blk[pg][j >> 4]), s_ulp_hist[pg]))
+                         : kind == 2 ? __double2float_rn(onehyp_trigarg(in.v, __int_as_float(w)))
+                                     : __int_as_float(w);
+        }
     }
     if (warp == 0 && lane == 0) {
         if (stale)
@@ -1342,6 +1744,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                    n_groups, n_exact, prof_n_stamp, prof_n_c, n_redone, prof_n_fe, prof_n_fm, prof_steps ? (double)prof_steps_cyc / prof_steps : 0.0, prof_steps, (double)(clock64() - prof_k0) / n,
                    (double)prof_pre / n_groups, (double)prof_wait / n_groups, (double)prof_steps_cyc / n_groups,
                    (double)(clock64() - prof_k0 - prof_pre - prof_wait - prof_steps_cyc) / n_groups);
+        if (c == 0)
+            printf("pll dbg one-hypothesis: groups %d (cut short %d), %.1f cyc/step over %d steps, exact blocks %d | groups without tables %d\n",
+                   prof_one_groups, prof_one_short, prof_one_steps ? (double)prof_one_cyc / prof_one_steps : 0.0, prof_one_steps, prof_one_exact, prof_checked);
 #endif
         st[6] = (float)(n_groups + 1000 * min(n_exact, 999));     // diagnostics of the last launch
         st[7] = s_flag[1] ? -1.0f : (float)n_redone;

@@ -498,6 +498,89 @@ FMRX_HD void predictor_step(const Consts &k, float c, float &integ, float &ph)
     integ = p_fmaf(k.ki, p_fmaf(-kq, 6.2831855f, d), integ);         // :163
 }
 
+// ---- the one-hypothesis ("1H") scheme: an exact-ORDER predictor --------------------------------
+//
+// Where phaseEst's float grid is coarse (|phaseEst| in the hundreds and beyond: modes 2/3, where the
+// reference hands the PLL if_fs*interp and phaseEst cancels w*trigOffset; any loop that locks onto something
+// other than the pilot, or onto nothing, and runs away) the loop filter (:163-164) rounds phaseEst so
+// coarsely that an errorD good to ~1e-7 reproduces phaseEst BIT FOR BIT almost always.  So k_pll's predictor
+// warp then runs the recurrence in the reference's own operation order with errorD = wrap(pi*(x < 0) - trigArg)
+// -- what atan2(x*(-sin t), x*cos t) is up to the float roundings of the feedback pair -- in float; the
+// candidate warps evaluate the exact phase detector for the trigArg that follows from each PREDICTED
+// phaseEst; warp 0 runs the exact loop filter on those errorDs and accepts a block iff its phaseEst
+// matched the prediction at every step.  By induction an accepted block IS the reference's trajectory.
+//
+// Large arguments never meet float arithmetic: per sample the I/O warps prepare (in double) a float P near
+// the phaseEst to come, S = w*trigOffset + P split into B = fl32(S) and r = fl32(S - B), and
+// c = fl32(wrap(pi*(x_next < 0) - B)).  Then with d = phaseEst (-) P (exact: the two are within a factor of two)
+//     trigArg = fl32(w*trigOffset + phaseEst) = fl32(S + d) = B (+) (r (+) d)     (up to a double rounding)
+//     z = trigArg (-) B                                    (exact; small while P tracks phaseEst)
+//     errorD of the next sample ~ wrap(c - z).
+struct OneHypIn {
+    float P, r, B, c;
+};
+
+FMRX_HD double wrap_pm_pi(double a)
+{
+    const double kq = p_add(p_add(p_mul(a, 0.15915494309189535), FMRX_RINT_MAGIC), -FMRX_RINT_MAGIC);
+    return p_fma(-kq, 2.4492935982947064e-16, p_fma(-kq, 6.283185307179586, a));
+}
+
+// v = w*trigOffset after the step; ph0 a phaseEst `ahead` steps before this one and slope its mean advance per
+// step lately; x_next the pilot sample the resulting angle is for.
+FMRX_HD OneHypIn onehyp_inputs(double v, float ph0, float slope, int ahead, float x_next)
+{
+    OneHypIn o;
+    o.P = p_d2f(p_fma((double)slope, (double)ahead, (double)ph0));
+    const double S = p_add(v, (double)o.P);
+    o.B = p_d2f(S);
+    o.r = p_d2f(p_add(S, -(double)o.B));
+    o.c = p_d2f(wrap_pm_pi(p_add(x_next < 0.0f ? 3.141592653589793 : 0.0, -(double)o.B)));
+    return o;
+}
+
+// the angle for the first sample of a group, from the exact trigArg before it
+FMRX_HD float onehyp_first_angle(float x, double tad)
+{
+    return p_d2f(wrap_pm_pi(p_add(x < 0.0f ? 3.141592653589793 : 0.0, -tad)));
+}
+
+// One predictor step: `a` is the angle (the approximate errorD) for this sample; returns the one for the next,
+// NOT reduced: while P tracks phaseEst and the loop is anywhere near lock it lies in [-pi, pi] as it is.  The
+// caller keeps the largest |angle| of a block of steps and, if that exceeded pi, runs the block again with
+// onehyp_predictor_step_reduced (a reduction on the dependent chain of every step would cost the common case
+// a third of its speed: k_pll's predictor warp sets the pace of a one-hypothesis group).
+FMRX_HD float onehyp_predictor_step(const Consts &k, const OneHypIn &in, float a, float &integ, float &ph)
+{
+    integ = p_faddf(integ, p_fmulf(k.ki, a));                        // :163
+    ph = p_faddf(ph, p_faddf(p_fmulf(k.kp, a), integ));              // :164
+    const float d = p_faddf(ph, -in.P);
+    const float y = p_faddf(in.r, d);
+    const float t = p_faddf(in.B, y);                                // :167 (trigArg)
+    const float z = p_faddf(t, -in.B);
+    return p_faddf(in.c, -z);
+}
+
+// The same step with the angle reduced to [-pi, pi]: c - z again with the whole turns taken out of z FIRST (z is
+// exact; c - z as formed above has lost its low bits to the turns).  2 pi = 6.2831855f - 1.7484555e-07f.
+FMRX_HD float onehyp_predictor_step_reduced(const Consts &k, const OneHypIn &in, float a, float &integ, float &ph)
+{
+    integ = p_faddf(integ, p_fmulf(k.ki, a));                        // :163
+    ph = p_faddf(ph, p_faddf(p_fmulf(k.kp, a), integ));              // :164
+    const float d = p_faddf(ph, -in.P);
+    const float y = p_faddf(in.r, d);
+    const float t = p_faddf(in.B, y);                                // :167 (trigArg)
+    const float z = p_faddf(t, -in.B);
+    const float an = p_faddf(in.c, -z);
+    const float kq = p_faddf(p_faddf(p_fmulf(an, 0.15915494f), 12582912.0f), -12582912.0f);
+    return p_fmaf(kq, 1.7484555e-07f, p_faddf(p_fmaf(-kq, 6.2831855f, -z), in.c));
+}
+
+#define FMRX_ONEHYP_PI 3.14159274f       /* fl32(pi): the largest |angle| the unreduced step may carry */
+
+// trigArg as the reference forms it (:167): fl32(w*trigOffset + (double)phaseEst), held in a double
+FMRX_HD double onehyp_trigarg(double v, float ph) { return (double)p_d2f(p_add(v, (double)ph)); }
+
 // trigOffset advances by float additions of 1 (:166).  From an integer-valued start
 // in [0, 2^24] the value after j steps is min(start + j, 2^24) exactly (2^24 + 1
 // rounds back to 2^24: the counter saturates), which lets the device prepare

@@ -5,6 +5,8 @@
 // Build: g++ -O2 -ffp-contract=off [-mfma] -shared -fPIC (tests/conftest.py).
 #include <cstddef>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include "fmrx_pll_core.h"
 
 using namespace pllcore;
@@ -483,6 +485,143 @@ extern "C" int pll_model_one_hypothesis(const float *pilot, int n, float freq, f
                     trig_out[base + tb + j] = (float)pt[tb + j];
             } else {
                 stats[1]++;
+                c = ck;
+                for (int j = 0; j < nb; j++)
+                    trig_out[base + tb + j] = chain_step(c, k, K, pilot[base + tb + j], nullptr);
+            }
+        }
+    }
+    state5[0] = c.integ; state5[1] = c.ph; state5[4] = c.toff;
+    chain_feedback(c, state5[2], state5[3]);
+    return 0;
+}
+
+// ---- the one-hypothesis scheme AS k_pll RUNS IT (float predictor), sequentially ------------------
+//
+// Same roles as the kernel (csrc/fmrx_kernels.cu, the "1H" groups), per group of 1024 steps:
+//   prepare  : per sample, from (integrator, phaseEst) at the start of the group TWO BEFORE (the I/O warps
+//              work two groups ahead) a float P near the phaseEst to come (linear extrapolation: the mean
+//              slope of phaseEst is the integrator), then with S = w*trigOffset + P in double:
+//              B = fl32(S), r = fl32(S - B), c' = fl32(wrap(pi*(x_next < 0) - B)).
+//              trigArg = fl32(w*trigOffset + phaseEst) = fl32(S + d), d = phaseEst (-) P  (exact: Sterbenz),
+//              is then B (+) (r (+) d), its distance from B is z = trigArg (-) B (small), and the phase
+//              detector's angle for the next sample wrap(c' - z): no large-argument reduction anywhere.
+//   predictor: FMUL + 8 dependent FADD per step in the reference's operation order (:163-164),
+//              restarted from the exact state at every group.
+//   candidates: the exact phase detector (make_feedback / error_from_feedback) for the trigArg the
+//              reference forms from the PREDICTED phaseEst of the step before (:167, in double).
+//   chain    : the exact loop filter on those errorDs; a block of 16 is accepted iff its phaseEst
+//              matched the predictor's bit for bit at every step (and every candidate guard held).
+// policy 0: a failed block is stepped the exact way and the comparison goes on (the predictor is not
+// restarted inside a group); policy 1: after a failed block the rest of the group is stepped exactly.
+// stats: [0] accepted blocks, [1] exact blocks, [2] groups with at least one failure.
+// per group of the last pll_model_onehyp_float run: |phaseEst| at its start and whether it had a failed block
+extern "C" {
+float pll_model_grp_ph[1 << 17];
+unsigned char pll_model_grp_fail[1 << 17];
+}
+
+extern "C" int pll_model_onehyp_float(const float *pilot, int n, float freq, float Fs, float bw, float *state5,
+                                      float *trig_out, long long *stats, int policy)
+{
+    Consts k;
+    k.kp = bw * 2.666f;
+    k.ki = (bw * bw) * 3.555f;
+    k.w = (2.0 * 3.14159265358979323846) * (double)(freq / Fs);
+    const TrigK K = trig_constants();
+    Chain c;
+    memset(&c, 0, sizeof(c));
+    c.integ = state5[0]; c.ph = state5[1]; c.fi = state5[2]; c.fq = state5[3]; c.toff = state5[4];
+    chain_load(c, k);
+    const int GROUP = 1024;
+    static float pph[GROUP];
+    static OneHypIn in1[GROUP];
+    static double v[GROUP];
+    auto bits = [](float f) { int i; memcpy(&i, &f, 4); return i; };
+    // (integ, ph) at the start of every group: prepare() for group g extrapolates from the start of group g - 2
+    // (the I/O warps work two groups ahead; the launch's initial state for the first two groups)
+    static float h_slope[1 << 17], h_ph[1 << 17];
+    for (int base = 0, g = 0; base < n; base += GROUP, g++) {
+        const int cnt = n - base < GROUP ? n - base : GROUP;
+        const bool regular = toff_is_regular(c.toff) && fabs(c.tad) <= FMRX_FAST_TRIG_MAX;
+        bool group_failed = false;
+        if (g < (1 << 17)) {
+            pll_model_grp_ph[g] = fabsf(c.ph);
+            pll_model_grp_fail[g] = 0;
+            h_slope[g] = g > 0 ? (c.ph + -h_ph[g - 1]) * (1.0f / GROUP) : c.integ;      // as k_pll's header: the slope over the group before
+            h_ph[g] = c.ph;
+        }
+        const int og = g >= 2 ? g - 2 : 0;
+        const float e_integ = h_slope[og], e_ph = h_ph[og];
+        const int e_age = (g - og) * GROUP;
+        if (regular) {
+            for (int j = 0; j < cnt; j++) {
+                v[j] = p_mul(k.w, (double)toff_after(c.toff, j + 1));
+                const float x_next = base + j + 1 < n ? pilot[base + j + 1] : 1.0f;
+                in1[j] = onehyp_inputs(v[j], e_ph, e_integ, e_age + j + 1, x_next);
+            }
+            // predictor
+            float pi_ = c.integ, pp = c.ph;
+            float a = onehyp_first_angle(pilot[base], c.tad);      // the angle from the exact trigArg before the group
+            for (int j0 = 0; j0 < cnt; j0 += 8) {          // as the predictor warp: blocks of 8, again with the reduction if an angle left [-pi, pi]
+                const float a0 = a, i0 = pi_, p0 = pp;
+                float amax = fabsf(a);
+                for (int j = j0; j < j0 + 8 && j < cnt; j++) {
+                    a = onehyp_predictor_step(k, in1[j], a, pi_, pp);
+                    pph[j] = pp;
+                    if (j + 1 < j0 + 8)
+                        amax = fmaxf(amax, fabsf(a));
+                }
+                if (!(amax <= FMRX_ONEHYP_PI)) {
+                    stats[3]++;                  // blocks of 8 predictor steps that needed the angle reduction
+                    a = a0; pi_ = i0; pp = p0;
+                    if (!(fabsf(a) <= FMRX_ONEHYP_PI))
+                        a = a - 6.2831855f * ((a * 0.15915494f + 12582912.0f) - 12582912.0f);
+                    for (int j = j0; j < j0 + 8 && j < cnt; j++) {
+                        a = onehyp_predictor_step_reduced(k, in1[j], a, pi_, pp);
+                        pph[j] = pp;
+                    }
+                }
+            }
+        }
+        for (int tb = 0; tb < cnt; tb += 16) {
+            const int nb = cnt - tb < 16 ? cnt - tb : 16;
+            const Chain ck = c;
+            float integ = c.integ, ph = c.ph;
+            int bad = (regular && !(policy == 1 && group_failed)) ? 0 : 1;
+            double tprev = c.tad;
+            for (int j = 0; j < nb && !bad; j++) {
+                const int u = tb + j;
+                const float x = pilot[base + u];
+                if (j > 0)
+                    tprev = onehyp_trigarg(v[u - 1], pph[u - 1]);       // :167 from the predicted phaseEst
+                bool ok = fabs(tprev) <= FMRX_FAST_TRIG_MAX;
+                const Feedback f = make_feedback(K, tprev, x < 0.0f ? 2.0 : 0.0, 1.0 / (double)x, nullptr, nullptr);
+                const float ed = error_from_feedback(f, x, (double)x, ok);
+                integ = integ + k.ki * ed;
+                ph = ph + (k.kp * ed + integ);
+                bad |= !ok;
+                bad |= bits(ph) ^ bits(pph[u]);
+                if (bad && getenv("PLL_MODEL_DEBUG") && fabsf(c.ph) > 30000.0f)
+                    fprintf(stderr, "fail g %d step %d ok %d ph %.9g pred %.9g (%d ulps) ed %.9g x %.4g tprev %.9g | in: P %.9g r %.9g B %.9g c %.9g\n", g, u, (int)ok, ph,
+                            pph[u], bits(ph) - bits(pph[u]), ed, x, tprev, in1[u].P, in1[u].r, in1[u].B, in1[u].c);
+            }
+            if (!bad) {
+                stats[0]++;
+                c.integ = integ;
+                c.ph = ph;
+                c.toff = toff_after(ck.toff, nb);
+                c.tad = onehyp_trigarg(v[tb + nb - 1], ph);
+                chain_refresh(c);
+                for (int j = 0; j < nb; j++)
+                    trig_out[base + tb + j] = (float)onehyp_trigarg(v[tb + j], pph[tb + j]);
+            } else {
+                stats[1]++;
+                if (!group_failed)
+                    stats[2]++;
+                group_failed = true;
+                if (g < (1 << 17))
+                    pll_model_grp_fail[g] = 1;
                 c = ck;
                 for (int j = 0; j < nb; j++)
                     trig_out[base + tb + j] = chain_step(c, k, K, pilot[base + tb + j], nullptr);

@@ -265,3 +265,31 @@ def test_one_hypothesis_scheme_is_exact(model, port, case, fs_pll, fs_sig, max_e
     assert_bits_equal(trig, otrig, f"trigArg ({case})")
     assert_bits_equal(st[:2], ost[:2], f"integrator, phaseEst ({case})")
     assert stats[1] <= max_exact * (stats[0] + stats[1]), stats.tolist()
+
+
+@pytest.mark.parametrize("mode,kind,seconds,max_exact", [(2, "stereo", 6.0, 0.03), (3, "stereo", 6.0, 0.05), (0, "nopilot", 4.0, 0.02),
+                                                         (0, "noise", 4.0, 0.06), (0, "offtune", 4.0, 0.02), (2, "noise", 4.0, 0.04)])
+def test_one_hypothesis_scheme_as_k_pll_runs_it(model, port, synth, mode, kind, seconds, max_exact):
+    """k_pll's one-hypothesis groups, sequentially on the host with the kernel's own arithmetic (fmrx_pll_core.h:
+    onehyp_inputs from a loop filter state two groups back, the float predictor in blocks of 8 with the deferred
+    angle reduction, the exact phase detector for the trigArg that follows from each predicted phaseEst, the exact
+    loop filter, a block accepted iff its phaseEst matched the prediction bit for bit): on the pilot the chain
+    extracts from modes 2/3 captures and from captures whose loop locks onto nothing or onto the wrong tone --
+    everything the three-hypothesis tables cannot serve -- trigArg, integrator and phaseEst are bit-identical to
+    the oracle and only a few per cent of the blocks need the exact step."""
+    info = port.mode(mode, 51)
+    nb = int(seconds * info.rf_fs * 2 / info.block_size)
+    iq = synth.synth_iq_exact(nb * info.block_size // 2, float(info.rf_fs), station=0, kind=kind)
+    _, d = port.chain(mode, 51).run(iq, ("pilot",))
+    x = d["pilot"]
+    fs_pll = float(info.if_fs)
+    model.pll_model_onehyp_float.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, f32p, f32p, C.POINTER(C.c_longlong), C.c_int]
+    st = np.array([0, 0, 1, 0, 0], np.float32)
+    stats = np.zeros(4, np.int64)
+    trig = np.zeros(len(x), np.float32)
+    model.pll_model_onehyp_float(x.ctypes.data_as(f32p), len(x), 19000.0, fs_pll, 0.01, st.ctypes.data_as(f32p),
+                                 trig.ctypes.data_as(f32p), stats.ctypes.data_as(C.POINTER(C.c_longlong)), 0)
+    _, otrig, ost = port.pll(x, 19000, fs_pll, 2, 0, 0.01)
+    assert_bits_equal(trig, otrig, f"trigArg (mode {mode}, {kind})")
+    assert_bits_equal(st[:2], ost[:2], f"integrator, phaseEst (mode {mode}, {kind})")
+    assert stats[1] <= max_exact * (stats[0] + stats[1]), stats.tolist()
