@@ -113,7 +113,9 @@ typedef struct {
     int device;            /* CUDA device ordinal; -1 = current */
     int chunk_blocks;      /* blocks per internal pipeline chunk; 0 = auto */
     int keep_stages;       /* 1 = retain per-stage intermediates for fmrx_read_stage */
-    int reserved[4];       /* must be 0 */
+    int n_sets;            /* chunk buffers in the internal ring; 0 = 3.  More lets the feed-forward stages
+                              (K1, K2) run that many chunks ahead of the PLL (time shards: fmrx_long_*) */
+    int reserved[3];       /* must be 0 */
 } fmrx_config;
 
 typedef struct {           /* src/project.cpp:304-364, derived */
@@ -202,6 +204,38 @@ uint64_t fmrx_kernel_launches(const fmrx_pipeline *p);
  * pipeline's streams.  out[4] = {rf+demod, band-pass pair, PLL, audio}. */
 int fmrx_set_timing(fmrx_pipeline *p, int enable);
 int fmrx_last_timing(fmrx_pipeline *p, float out_ms[4]);
+
+/* ---------------------------------------------------------------------- */
+/* One long capture, time-sharded over several devices of one box           */
+/* (the reference's block loop, src/project.cpp:48-84,      */
+/* 132-196, run on consecutive pieces of ONE stream)                        */
+/* ---------------------------------------------------------------------- */
+/* The capture is cut into n_shards consecutive runs of whole blocks, shard r
+ * on devices[r] (an ordinal may repeat: several shards on one device).  The
+ * feed-forward stages of every shard run at once, each from a halo of blocks
+ * in front of its own; the PLL recurrence runs shard after shard, its state
+ * handed from device to device; the PCM is gathered on devices[0].  The
+ * result is bit-identical to one pipeline processing the whole capture. */
+typedef struct fmrx_long_capture fmrx_long_capture;
+int fmrx_long_create(fmrx_long_capture **out, int mode, int taps, int n_shards,
+                     const int *devices, size_t n_blocks_total);
+int fmrx_long_destroy(fmrx_long_capture *h);
+/* Blocks of shard `shard`: its first block, its length, and how many blocks in
+ * front of it its halo takes (0 for the first shard). */
+int fmrx_long_shard(const fmrx_long_capture *h, int shard, size_t *first_block,
+                    size_t *n_blocks, size_t *halo_blocks);
+/* HOST buffers: iq = the whole capture (n_blocks_total*block_size u8), pcm =
+ * the whole output (n_blocks_total*2*audio_per_block int16). */
+int fmrx_long_process(fmrx_long_capture *h, const uint8_t *iq, int16_t *pcm);
+/* DEVICE buffers: iq_dev[r] on devices[r] points at the first HALO block of
+ * shard r (halo and shard contiguous); pcm_dev0 on devices[0] receives the
+ * whole PCM.  Returns when it is complete. */
+int fmrx_long_process_device(fmrx_long_capture *h, const uint8_t *const *iq_dev,
+                             int16_t *pcm_dev0);
+/* Device time of the last fmrx_long_process_device call, milliseconds. */
+int fmrx_long_last_ms(const fmrx_long_capture *h, float *ms);
+/* The six PLL scalars after the last shard (fmrx_pll's order). */
+int fmrx_long_pll_state(fmrx_long_capture *h, float out[6]);
 
 #ifdef __cplusplus
 }

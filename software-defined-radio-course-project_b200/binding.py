@@ -39,6 +39,8 @@ ABI_SYMBOLS = (
     "fmrx_state_size", "fmrx_get_state", "fmrx_set_state", "fmrx_get_pll_state",
     "fmrx_host_alloc", "fmrx_host_free", "fmrx_kernel_launches", "fmrx_set_timing",
     "fmrx_last_timing",
+    "fmrx_long_create", "fmrx_long_destroy", "fmrx_long_shard", "fmrx_long_process", "fmrx_long_process_device",
+    "fmrx_long_last_ms", "fmrx_long_pll_state",
 )
 
 
@@ -56,7 +58,7 @@ class ModeInfoStruct(C.Structure):
 
 class ConfigStruct(C.Structure):
     _fields_ = [("mode", C.c_int), ("taps", C.c_int), ("n_captures", C.c_int), ("device", C.c_int),
-                ("chunk_blocks", C.c_int), ("keep_stages", C.c_int), ("reserved", C.c_int * 4)]
+                ("chunk_blocks", C.c_int), ("keep_stages", C.c_int), ("n_sets", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class ModeInfo:
@@ -110,6 +112,13 @@ def load() -> C.CDLL:
     L.fmrx_host_free.argtypes = [C.c_void_p]
     L.fmrx_kernel_launches.argtypes = [C.c_void_p]
     L.fmrx_kernel_launches.restype = C.c_uint64
+    L.fmrx_long_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_size_t]
+    L.fmrx_long_destroy.argtypes = [C.c_void_p]
+    L.fmrx_long_shard.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.fmrx_long_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fmrx_long_process_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+    L.fmrx_long_last_ms.argtypes = [C.c_void_p, _f32p]
+    L.fmrx_long_pll_state.argtypes = [C.c_void_p, _f32p]
     L.fmrx_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.fmrx_last_timing.argtypes = [C.c_void_p, _f32p]
     _lib = L
@@ -324,3 +333,58 @@ class Pipeline:
         _check(self._L.fmrx_last_timing(self._h, _fp(t)), "fmrx_last_timing")
         return {"rf_demod_ms": float(t[0]), "bandpass_ms": float(t[1]), "pll_ms": float(t[2]),
                 "audio_ms": float(t[3])}
+
+
+class LongCapture:
+    """One long capture time-sharded over the devices of one box (fmrx_long_*): shard r on ``devices[r]``; the
+    feed-forward stages of all shards run at once from FIR halos, the PLL state is handed from shard to shard,
+    the PCM is gathered on ``devices[0]``.  Bit-identical to one ``Pipeline`` over the whole capture."""
+
+    def __init__(self, mode: int, taps: int, devices, n_blocks: int):
+        self._L = load()
+        self.devices = list(devices)
+        self.n_blocks = int(n_blocks)
+        self.info = mode_table(mode, taps)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        _check(self._L.fmrx_long_create(C.byref(h), mode, taps, len(self.devices), arr, self.n_blocks), "fmrx_long_create")
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._L.fmrx_long_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def shard(self, r: int):
+        """(first block, blocks, halo blocks) of shard r."""
+        a, b, c = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        _check(self._L.fmrx_long_shard(self._h, r, C.byref(a), C.byref(b), C.byref(c)), "fmrx_long_shard")
+        return a.value, b.value, c.value
+
+    def process(self, iq: np.ndarray) -> np.ndarray:
+        """Host buffers: the whole capture (uint8) in, the whole PCM (int16, R,L interleaved) out."""
+        iq = np.ascontiguousarray(iq, np.uint8)
+        assert iq.size >= self.n_blocks * self.info.block_size
+        pcm = np.zeros(self.n_blocks * 2 * self.info.audio_per_block, np.int16)
+        _check(self._L.fmrx_long_process(self._h, iq.ctypes.data, pcm.ctypes.data), "fmrx_long_process")
+        return pcm
+
+    def process_device(self, iq_ptrs, pcm_ptr0: int) -> float:
+        """Device pointers: ``iq_ptrs[r]`` on ``devices[r]`` at the first halo block of shard r; ``pcm_ptr0`` on
+        ``devices[0]``.  Returns the device time of the call in milliseconds."""
+        arr = (C.c_void_p * len(self.devices))(*iq_ptrs)
+        _check(self._L.fmrx_long_process_device(self._h, arr, pcm_ptr0), "fmrx_long_process_device")
+        ms = np.zeros(1, np.float32)
+        _check(self._L.fmrx_long_last_ms(self._h, _fp(ms)), "fmrx_long_last_ms")
+        return float(ms[0])
+
+    def pll_state(self) -> np.ndarray:
+        st = np.zeros(6, np.float32)
+        _check(self._L.fmrx_long_pll_state(self._h, _fp(st)), "fmrx_long_pll_state")
+        return st

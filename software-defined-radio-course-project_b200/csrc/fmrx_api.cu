@@ -45,11 +45,66 @@ int cuda_fail(cudaError_t e, const char *what)
             return cuda_fail(e_, #call);                    \
     } while (0)
 
-// Small RAII device buffer for the operator entry points.
+// Device scratch of the operator entry points: a per-thread arena that only ever grows, so that a block loop
+// calling the operators (the unmodified reference main linked against host/filter_shim.cpp does: eleven calls
+// per block, src/project.cpp:65-175) pays for cudaMalloc / cudaFree once and not forty times per block.
+// A DevBuf takes the next slot of the calling thread's arena for the duration of one entry point.
+struct Arena {
+    static constexpr int kSlots = 6;
+    void *p[kSlots] = {};
+    size_t cap[kSlots] = {};
+    int device = -1, used = 0;
+    ~Arena() { release(); }
+    void release()
+    {
+        for (int i = 0; i < kSlots; i++) {
+            if (p[i])
+                cudaFree(p[i]);      // (after the context has gone at process exit this fails, harmlessly)
+            p[i] = nullptr;
+            cap[i] = 0;
+        }
+    }
+};
+thread_local Arena g_arena;
+
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    int slot = -1;
+    DevBuf() { slot = g_arena.used < Arena::kSlots ? g_arena.used++ : -1; }
+    ~DevBuf()
+    {
+        if (slot >= 0)
+            g_arena.used--;
+        else if (p)
+            cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes)
+    {
+        bytes = bytes ? bytes : 1;
+        if (slot < 0)
+            return cudaMalloc(&p, bytes);
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess)
+            return e;
+        if (dev != g_arena.device) {
+            g_arena.release();
+            g_arena.device = dev;
+        }
+        if (g_arena.cap[slot] < bytes) {
+            if (g_arena.p[slot])
+                cudaFree(g_arena.p[slot]);
+            g_arena.p[slot] = nullptr;
+            g_arena.cap[slot] = 0;
+            const size_t want = bytes + bytes / 2;       // (some headroom: block sizes vary by a few taps)
+            e = cudaMalloc(&g_arena.p[slot], want);
+            if (e != cudaSuccess)
+                return e;
+            g_arena.cap[slot] = want;
+        }
+        p = g_arena.p[slot];
+        return cudaSuccess;
+    }
     template <class T> T *as() { return static_cast<T *>(p); }
 };
 
@@ -278,7 +333,7 @@ extern "C" int fmrx_pcm_pack(int16_t *pcm, const float *left, const float *right
 // ---------------------------------------------------------------------------
 
 namespace {
-constexpr int kSets = 3;
+constexpr int kDefaultSets = 3;
 constexpr uint32_t kStateMagic = 0x58524d46u;   // "FMRX"
 
 struct StateHeader {
@@ -316,7 +371,7 @@ struct fmrx_pipeline {
     uint8_t *d_hist_iq = nullptr;                         // [C][2*hist_pairs]
     float *d_tail_demod = nullptr, *d_tail_chan = nullptr, *d_tail_trig = nullptr;   // [C][H]
     float *d_pll_state = nullptr;                         // [C][8]
-    BufferSet sets[kSets];
+    std::vector<BufferSet> sets;    // the ring of chunk buffers (fmrx_config.n_sets; 3 by default)
     cudaStream_t s_front = nullptr, s_pll = nullptr, s_back = nullptr;
     cudaStream_t s_h2d = nullptr;   // host path: the H2D copies, so that chunk i+1 comes in under K1/K2 of chunk i
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -395,6 +450,7 @@ int create_impl(fmrx_pipeline *p, const fmrx_config *cfg)
     const int T = mi.taps, U = mi.audio_interp, D = mi.audio_decim;
     p->C = cfg->n_captures;
     p->keep_stages = cfg->keep_stages != 0;
+    p->sets.resize(cfg->n_sets > 0 ? cfg->n_sets : kDefaultSets);
     const size_t C = p->C;
 
     // history: band-pass needs T-1; the audio stage needs T-1 + 5 delayed frames
@@ -524,8 +580,10 @@ cudaError_t copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, siz
 }
 
 // The chunk loop shared by the host- and device-pointer entry points.
+// feedforward_only: K1 and K2 only -- what a time shard runs over the blocks in FRONT of its own (its halo), from the
+// zero state, to arrive at the IQ / demod / channel histories the stream has at the shard's first block.
 int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, int16_t *pcm,
-        size_t pcm_stride, bool host_io, cudaStream_t user)
+        size_t pcm_stride, bool host_io, cudaStream_t user, bool feedforward_only = false)
 {
     const fmrx_mode_info &mi = p->mi;
     const int C = p->C, T = mi.taps, H = p->H;
@@ -579,7 +637,7 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
         const int n_if = nb * mi.if_per_block;
         const size_t chunk_bytes = static_cast<size_t>(nb) * mi.block_size;
         const size_t chunk_pcm = static_cast<size_t>(nb) * 2 * mi.audio_per_block;
-        BufferSet &S = p->sets[p->chunk_counter % kSets];
+        BufferSet &S = p->sets[p->chunk_counter % p->sets.size()];
         cudaEvent_t *te = p->timing ? &p->tev[tev0 + 8 * ci] : nullptr;
 
         // ---------------- front: [H2D] K1 K2 ----------------
@@ -656,6 +714,12 @@ int run(fmrx_pipeline *p, const uint8_t *iq, size_t iq_stride, size_t n_blocks, 
         CU(copy2d(p->d_tail_demod, fH, S.demod + n_if, if_pitch, fH, C, p->s_front));
         CU(copy2d(p->d_tail_chan, fH, S.chan + n_if, if_pitch, fH, C, p->s_front));
         CU(cudaEventRecord(S.front_done, p->s_front));
+        if (feedforward_only) {
+            CU(cudaEventRecord(S.free_ev, p->s_front));
+            S.free_pending = true;
+            p->chunk_counter++;
+            continue;
+        }
 
         // ---------------- pll: K3 ----------------
         CU(cudaStreamWaitEvent(p->s_pll, S.front_done, 0));
@@ -787,6 +851,8 @@ extern "C" int fmrx_create(fmrx_pipeline **out, const fmrx_config *cfg)
     for (int r : cfg->reserved)
         if (r != 0)
             return FMRX_ERR_ARG;
+    if (cfg->n_sets < 0 || cfg->n_sets == 1 || cfg->n_sets > 64)
+        return FMRX_ERR_ARG;
     *out = nullptr;
     fmrx_mode_info mi;
     if (fmrx_mode_table(cfg->mode, cfg->taps, &mi) != FMRX_OK)
@@ -1018,4 +1084,269 @@ extern "C" int fmrx_last_timing(fmrx_pipeline *p, float out_ms[4])
     }
     std::memcpy(out_ms, p->last_ms, sizeof(p->last_ms));
     return FMRX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// One long capture, time-sharded over several devices (BASELINE.json configs[4])
+// ---------------------------------------------------------------------------
+//
+// The capture is cut into consecutive runs of whole blocks, one per device.  What shards in time is everything
+// feed-forward: K1 and K2 have finite memory, so a shard that runs them over a HALO of blocks in front of its own
+// (from the zero state) arrives at exactly the IQ / demod / channel histories the stream has at its first block,
+// and then runs K1/K2 of its whole shard at once -- every device at the same time, nothing waiting for anybody.
+// What does not shard is the PLL recurrence (one dependent chain per capture; speculative restarts never re-merge
+// bit for bit: DESIGN.md 4.1): K3 of shard r starts when K3 of shard r-1 has finished, from its state -- the PLL
+// scalars and the trigArg history K4's mixer tail needs, ~1.5 KB, moved with cudaMemcpyPeerAsync straight into
+// shard r's pipeline and ordered with an event; K4 follows K3 per shard.  The PCM of every shard is gathered on
+// the first device with peer copies (NVLink where the devices have it).  All of it is enqueued from one host
+// thread without a single host synchronisation until the end.
+
+struct fmrx_long_capture {
+    fmrx_mode_info mi{};
+    int n = 0;                                   // shards
+    size_t n_blocks = 0;
+    int halo_blocks = 0;
+    std::vector<int> device;
+    std::vector<fmrx_pipeline *> pipe;
+    std::vector<size_t> first, count;            // blocks of each shard
+    std::vector<int16_t *> d_pcm;                // per shard, on its device
+    std::vector<uint8_t *> d_iq;                 // host path: halo + shard staged on each device
+    std::vector<cudaEvent_t> handed;             // shard r's PLL state has arrived in shard r+1's pipeline
+    std::vector<cudaStream_t> s_io;              // per device: staging copies
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    float last_ms = 0.0f;
+};
+
+namespace {
+void free_long(fmrx_long_capture *L)
+{
+    if (!L)
+        return;
+    for (int r = 0; r < L->n; r++) {
+        if (r < (int)L->device.size())
+            cudaSetDevice(L->device[r]);
+        if (r < (int)L->d_pcm.size() && L->d_pcm[r]) cudaFree(L->d_pcm[r]);
+        if (r < (int)L->d_iq.size() && L->d_iq[r]) cudaFree(L->d_iq[r]);
+        if (r < (int)L->handed.size() && L->handed[r]) cudaEventDestroy(L->handed[r]);
+        if (r < (int)L->s_io.size() && L->s_io[r]) cudaStreamDestroy(L->s_io[r]);
+        if (r < (int)L->pipe.size() && L->pipe[r]) fmrx_destroy(L->pipe[r]);
+    }
+    if (L->n) cudaSetDevice(L->device[0]);
+    if (L->t0) cudaEventDestroy(L->t0);
+    if (L->t1) cudaEventDestroy(L->t1);
+    delete L;
+}
+}  // namespace
+
+extern "C" int fmrx_long_create(fmrx_long_capture **out, int mode, int taps, int n_shards, const int *devices,
+                                size_t n_blocks_total)
+{
+    if (!out || n_shards < 1 || n_shards > 64 || !devices || n_blocks_total < static_cast<size_t>(n_shards))
+        return FMRX_ERR_ARG;
+    *out = nullptr;
+    fmrx_mode_info mi;
+    if (fmrx_mode_table(mode, taps, &mi) != FMRX_OK)
+        return FMRX_ERR_ARG;
+    if (fmrx_device_count() < 1) {
+        std::snprintf(g_err, sizeof(g_err), "no CUDA device");
+        return FMRX_ERR_NO_DEVICE;
+    }
+    fmrx_long_capture *L = new (std::nothrow) fmrx_long_capture();
+    if (!L)
+        return FMRX_ERR_ALLOC;
+    L->mi = mi;
+    L->n = n_shards;
+    L->n_blocks = n_blocks_total;
+    L->device.assign(devices, devices + n_shards);
+    L->pipe.assign(n_shards, nullptr);
+    L->d_pcm.assign(n_shards, nullptr);
+    L->d_iq.assign(n_shards, nullptr);
+    L->handed.assign(n_shards, nullptr);
+    L->s_io.assign(n_shards, nullptr);
+    // The halo: IF samples of history the feed-forward stages must have RIGHT at the shard's first block are
+    // H (what every IF-rate array keeps in front); the channel filter reaches T-1 further back into demod, the RF
+    // filter (T-1)/decim + 2 IF samples further into the IQ.  In whole blocks:
+    const int T = mi.taps, U = mi.audio_interp, D = mi.audio_decim;
+    const int H = ((T + (kMonoDelay * D + U - 1) / U + 8 + 31) / 32) * 32;
+    const int need_if = H + (T - 1) + (T - 1) / mi.rf_decim + 2;
+    L->halo_blocks = (need_if + mi.if_per_block - 1) / mi.if_per_block;
+    const size_t base = n_blocks_total / n_shards, extra = n_blocks_total % n_shards;
+    size_t at = 0, longest = 0;
+    for (int r = 0; r < n_shards; r++) {
+        const size_t cnt = base + (static_cast<size_t>(r) < extra ? 1 : 0);
+        L->first.push_back(at);
+        L->count.push_back(cnt);
+        longest = std::max(longest, cnt);
+        at += cnt;
+    }
+    auto fail = [&](int rc) {
+        free_long(L);
+        return rc;
+    };
+    // chunks as large as a launch may be, and enough buffer sets for the feed-forward stages of the whole shard to
+    // run ahead of the PLL
+    const long long cb_max = std::min<long long>(((1ll << 26) - 1) / mi.if_per_block, ((1ll << 31) - 1) / mi.block_size);
+    const size_t target_if = (256u << 20) / sizeof(float);                      // ~256 MiB per IF-rate array per chunk
+    const size_t cb = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(static_cast<size_t>(cb_max), target_if / mi.if_per_block), longest));
+    const int n_sets = static_cast<int>(std::min<size_t>(64, std::max<size_t>(2, (longest + cb - 1) / cb + 1)));
+    for (int r = 0; r < n_shards; r++) {
+        fmrx_config cfg{};
+        cfg.mode = mode;
+        cfg.taps = taps;
+        cfg.n_captures = 1;
+        cfg.device = devices[r];
+        cfg.chunk_blocks = static_cast<int>(cb);
+        cfg.n_sets = n_sets;
+        int rc = fmrx_create(&L->pipe[r], &cfg);
+        if (rc != FMRX_OK)
+            return fail(rc);
+        if (cudaMalloc(reinterpret_cast<void **>(&L->d_pcm[r]), L->count[r] * 2 * mi.audio_per_block * sizeof(int16_t)) != cudaSuccess)
+            return fail(FMRX_ERR_ALLOC);
+        if (cudaEventCreateWithFlags(&L->handed[r], cudaEventDisableTiming) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&L->s_io[r], cudaStreamNonBlocking) != cudaSuccess)
+            return fail(FMRX_ERR_CUDA);
+        // direct peer copies between neighbouring shards and to the gathering device, where the hardware has them
+        for (int o : { r > 0 ? devices[r - 1] : devices[r], devices[0] }) {
+            int can = 0;
+            if (o != devices[r] && cudaDeviceCanAccessPeer(&can, devices[r], o) == cudaSuccess && can)
+                if (cudaDeviceEnablePeerAccess(o, 0) != cudaSuccess)
+                    cudaGetLastError();      // (already enabled)
+        }
+    }
+    cudaSetDevice(devices[0]);
+    if (cudaEventCreate(&L->t0) != cudaSuccess || cudaEventCreate(&L->t1) != cudaSuccess)
+        return fail(FMRX_ERR_CUDA);
+    *out = L;
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_long_destroy(fmrx_long_capture *L)
+{
+    free_long(L);
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_long_shard(const fmrx_long_capture *L, int shard, size_t *first_block, size_t *n_blocks, size_t *halo_blocks)
+{
+    if (!L || shard < 0 || shard >= L->n)
+        return FMRX_ERR_ARG;
+    if (first_block) *first_block = L->first[shard];
+    if (n_blocks) *n_blocks = L->count[shard];
+    if (halo_blocks) *halo_blocks = shard ? std::min<size_t>(L->halo_blocks, L->first[shard]) : 0;
+    return FMRX_OK;
+}
+
+// iq_dev[r]: on shard r's device, the first HALO block of shard r (block first[r] - halo[r] of the capture), halo
+// and shard contiguous.  pcm_dev0: on the first shard's device, the whole capture's PCM.
+extern "C" int fmrx_long_process_device(fmrx_long_capture *L, const uint8_t *const *iq_dev, int16_t *pcm_dev0)
+{
+    if (!L || !iq_dev || !pcm_dev0)
+        return FMRX_ERR_ARG;
+    const fmrx_mode_info &mi = L->mi;
+    const size_t pcm_per_block = 2 * static_cast<size_t>(mi.audio_per_block);
+    for (int r = 0; r < L->n; r++) {
+        CU(cudaSetDevice(L->device[r]));
+        const int rc = fmrx_reset(L->pipe[r]);
+        if (rc != FMRX_OK)
+            return rc;
+    }
+    CU(cudaSetDevice(L->device[0]));
+    CU(cudaEventRecord(L->t0, L->pipe[0]->s_front));
+    for (int r = 0; r < L->n; r++) {
+        fmrx_pipeline *p = L->pipe[r];
+        CU(cudaSetDevice(L->device[r]));
+        size_t halo = 0;
+        fmrx_long_shard(L, r, nullptr, nullptr, &halo);
+        if (!iq_dev[r])
+            return FMRX_ERR_ARG;
+        // the feed-forward histories at the shard's first block, from the halo (K1, K2 only; front stream)
+        if (halo) {
+            const int rc = run(p, iq_dev[r], halo * mi.block_size, halo, nullptr, 0, false, p->s_front, true);
+            if (rc != FMRX_OK)
+                return rc;
+        }
+        // the PLL-dependent state arrives from shard r-1 (enqueued there, below); K3 and K4 of this shard wait for it,
+        // K1 and K2 do not
+        if (r > 0) {
+            CU(cudaStreamWaitEvent(p->s_pll, L->handed[r - 1], 0));
+            CU(cudaStreamWaitEvent(p->s_back, L->handed[r - 1], 0));
+        }
+        // (run() orders its three streams after `user` and makes `user` wait for them: the shard's own I/O stream, so
+        // that nothing here waits for anything but what it needs)
+        {
+            const int rc = run(p, iq_dev[r] + halo * mi.block_size, L->count[r] * mi.block_size, L->count[r], L->d_pcm[r],
+                               L->count[r] * pcm_per_block, false, L->s_io[r]);
+            if (rc != FMRX_OK)
+                return rc;
+        }
+        // hand the PLL state on: behind this shard's last K3 (and its trigArg tail copy) on the PLL stream
+        if (r + 1 < L->n) {
+            fmrx_pipeline *q = L->pipe[r + 1];
+            CU(cudaMemcpyPeerAsync(q->d_pll_state, L->device[r + 1], p->d_pll_state, L->device[r], 8 * sizeof(float), p->s_pll));
+            CU(cudaMemcpyPeerAsync(q->d_tail_trig, L->device[r + 1], p->d_tail_trig, L->device[r],
+                                   static_cast<size_t>(p->H) * sizeof(float), p->s_pll));
+            CU(cudaEventRecord(L->handed[r], p->s_pll));
+        }
+        // gather: this shard's PCM to the first device, behind its K4
+        CU(cudaMemcpyPeerAsync(pcm_dev0 + L->first[r] * pcm_per_block, L->device[0], L->d_pcm[r], L->device[r],
+                               L->count[r] * pcm_per_block * sizeof(int16_t), L->s_io[r]));
+    }
+    for (int r = 0; r < L->n; r++) {
+        CU(cudaSetDevice(L->device[r]));
+        CU(cudaStreamSynchronize(L->s_io[r]));
+        CU(cudaStreamSynchronize(L->pipe[r]->s_pll));
+    }
+    CU(cudaSetDevice(L->device[0]));
+    CU(cudaEventRecord(L->t1, L->pipe[0]->s_front));
+    CU(cudaEventSynchronize(L->t1));
+    CU(cudaEventElapsedTime(&L->last_ms, L->t0, L->t1));
+    return FMRX_OK;
+}
+
+// HOST buffers: the whole capture in, the whole PCM out (pinned buffers make the staging copies asynchronous).
+extern "C" int fmrx_long_process(fmrx_long_capture *L, const uint8_t *iq, int16_t *pcm)
+{
+    if (!L || !iq || !pcm)
+        return FMRX_ERR_ARG;
+    const fmrx_mode_info &mi = L->mi;
+    std::vector<const uint8_t *> ptr(L->n, nullptr);
+    for (int r = 0; r < L->n; r++) {
+        CU(cudaSetDevice(L->device[r]));
+        size_t halo = 0;
+        fmrx_long_shard(L, r, nullptr, nullptr, &halo);
+        const size_t bytes = (halo + L->count[r]) * mi.block_size;
+        if (!L->d_iq[r])
+            CU(cudaMalloc(reinterpret_cast<void **>(&L->d_iq[r]), bytes));
+        CU(cudaMemcpyAsync(L->d_iq[r], iq + (L->first[r] - halo) * mi.block_size, bytes, cudaMemcpyHostToDevice, L->s_io[r]));
+        ptr[r] = L->d_iq[r];
+    }
+    for (int r = 0; r < L->n; r++) {
+        CU(cudaSetDevice(L->device[r]));
+        CU(cudaStreamSynchronize(L->s_io[r]));
+    }
+    CU(cudaSetDevice(L->device[0]));
+    int16_t *d_all = nullptr;
+    const size_t n_pcm = L->n_blocks * 2 * mi.audio_per_block;
+    CU(cudaMalloc(reinterpret_cast<void **>(&d_all), n_pcm * sizeof(int16_t)));
+    int rc = fmrx_long_process_device(L, ptr.data(), d_all);
+    if (rc == FMRX_OK && cudaMemcpy(pcm, d_all, n_pcm * sizeof(int16_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = FMRX_ERR_CUDA;
+    cudaFree(d_all);
+    return rc;
+}
+
+/* Device time of the last fmrx_long_process_device call: from the first enqueue to the gathered PCM. */
+extern "C" int fmrx_long_last_ms(const fmrx_long_capture *L, float *ms)
+{
+    if (!L || !ms)
+        return FMRX_ERR_ARG;
+    *ms = L->last_ms;
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_long_pll_state(fmrx_long_capture *L, float out[6])
+{
+    if (!L || !out)
+        return FMRX_ERR_ARG;
+    return fmrx_get_pll_state(L->pipe[L->n - 1], 0, out);
 }

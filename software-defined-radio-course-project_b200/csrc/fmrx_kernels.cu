@@ -263,67 +263,123 @@ cudaError_t launch_rf_demod(const RfDemodArgs &a, int n_captures, cudaStream_t s
 // ============================================================================
 // K2: pilot + stereo-band band-pass pair (no decimation)
 // ============================================================================
-// One shared demod tile feeds both filters: per staged sample 2 MACs.
+// One staged demod tile feeds both filters.  A thread owns R = 8 consecutive outputs n..n+7; tap k of output
+// n+i reads x[n + i - k], so over a group of four taps the eight outputs touch an 11-sample window that moves
+// down by four samples per group: the window lives in a circular buffer of three register quads and every
+// group brings in ONE new quad (an aligned LDS.128) plus the two filters' four taps (two broadcast LDS.128)
+// for 64 FMUL + 64 FADD.  The tap loop is unrolled over one trip round the buffer (12 taps) so that every
+// register index is static; T is padded to a multiple of 12 with zero taps (acc + 0*x is a bit-exact no-op for
+// finite x; the IF arrays carry enough history in front for the extra reads).  Each accumulator still sees its
+// products in ascending tap order (src/filter.cpp:84-92).  The tile is stored with one quad of padding after
+// every 8 samples, so the lane stride of the quad loads is 48 bytes: conflict-free.
 
-constexpr int BP_THREADS = 256;
-constexpr int BP_R = 4;
+constexpr int BP_THREADS = 128;
+constexpr int BP_R = 8;
 constexpr int BP_TILE = BP_THREADS * BP_R;              // 1024 outputs per tile
+constexpr int BP_UNROLL = 12;                           // taps per trip: three quads
+
+static inline int bp_tpad(int T) { return (T + BP_UNROLL - 1) / BP_UNROLL * BP_UNROLL; }
+// staged samples: outputs n0..n0+1023 need x[n0 - (Tpad-1) .. n0 + 1023], plus the front quad alignment
+// samples staged in front of n0 (a multiple of 8): the Tpad - 1 the taps reach back, and the quad the loop loads past them
+static inline int bp_front(int T) { return (bp_tpad(T) + 4 + 7) / 8 * 8; }
+static inline size_t bp_smem_bytes(int T)
+{
+    const int staged = bp_front(T) + BP_TILE;            // a multiple of 8
+    return sizeof(float) * ((size_t)staged / 8 * 12 + 2 * (size_t)bp_tpad(T));
+}
 
 __global__ void __launch_bounds__(BP_THREADS) k_bandpass_pair(const BandpassArgs a)
 {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int T = a.T;
-    float *s_x = smem;                       // [BP_TILE + T - 1]
-    float *s_p = s_x + BP_TILE + T - 1;      // [T] pilot taps
-    float *s_c = s_p + T;                    // [T] channel taps
+    const int Tpad = (T + BP_UNROLL - 1) / BP_UNROLL * BP_UNROLL;
+    const int front = (Tpad + 4 + 7) / 8 * 8;
+    const int staged = front + BP_TILE;
+    float *s_x = smem;                           // [staged/8][12]: 8 samples + one quad of padding
+    float *s_p = s_x + staged / 8 * 12;          // [Tpad] pilot taps
+    float *s_c = s_p + Tpad;                     // [Tpad] channel taps
 
     const int c = blockIdx.y, tid = threadIdx.x;
     const int n0 = blockIdx.x * BP_TILE;
     const float *demod = a.demod + (size_t)c * a.if_stride + a.if_off;
 
-    for (int k = tid; k < T; k += BP_THREADS) {
-        s_p[k] = a.taps_pilot[k];
-        s_c[k] = a.taps_chan[k];
+    for (int k = tid; k < Tpad; k += BP_THREADS) {
+        s_p[k] = k < T ? a.taps_pilot[k] : 0.0f;
+        s_c[k] = k < T ? a.taps_chan[k] : 0.0f;
     }
-    for (int l = tid; l < BP_TILE + T - 1; l += BP_THREADS) {
-        const int n = n0 - (T - 1) + l;      // >= -(T-1): history in front of if_off
-        s_x[l] = (n < a.n_if) ? demod[n] : 0.0f;
+    // staged sample l (0..staged) is x[n0 - front + l]; history in front of if_off is real data (or the zeros of a
+    // fresh stream) as far back as the arrays go: -if_off
+    for (int l = tid; l < staged; l += BP_THREADS) {
+        const int n = n0 - front + l;
+        s_x[l + (l >> 3) * 4] = (n < a.n_if && n >= -a.if_off) ? demod[n] : 0.0f;
     }
     __syncthreads();
 
+    // this thread's outputs n0 + 8 tid + i.  Window quad q holds x[base - 4 q .. base - 4 q + 3] with
+    // base = n0 + 8 tid + 4 (staged index front + 8 tid + 4): quads 0 and 1 are the thread's own 8 samples.
+    const float4 *xq = reinterpret_cast<const float4 *>(s_x);
+    // staged index of the first sample of quad q: l = front + 8 tid + 4 - 4 q, a multiple of 4; its float4 slot
+    // is (l / 8) * 3 + (l % 8) / 4
+    auto quad = [&](int q) -> float4 {
+        const int l = front + 8 * tid + 4 - 4 * q;
+        return xq[(l >> 3) * 3 + ((l >> 2) & 1)];
+    };
+    float4 w0 = quad(0), w1 = quad(1), w2 = quad(2);        // w0: x[n+4..n+7], w1: x[n..n+3], w2: x[n-4..n-1]
     float ap[BP_R], ac[BP_R];
 #pragma unroll
-    for (int r = 0; r < BP_R; r++) {
-        ap[r] = 0.0f;
-        ac[r] = 0.0f;
+    for (int i = 0; i < BP_R; i++) {
+        ap[i] = 0.0f;
+        ac[i] = 0.0f;
     }
-    for (int k = 0; k < T; k++) {
-        const float cp = s_p[k], cc = s_c[k];
-        const int idx = tid + (T - 1 - k);
+    // One group of four taps k..k+3 with the window (hi, mid, lo) = samples x[m+4..m+7], x[m..m+3], x[m-4..m-1],
+    // m = n - k: output i = 4 h + j (h = 0, 1) at tap k + t reads x[n + i - k - t] = x[m + i - t].
+    auto group4 = [&](const float4 &hi, const float4 &mid, const float4 &lo, const float4 &cp, const float4 &cc) {
+        const float xs[12] = { lo.x, lo.y, lo.z, lo.w, mid.x, mid.y, mid.z, mid.w, hi.x, hi.y, hi.z, hi.w };   // x[m-4 .. m+7]
+        const float tp[4] = { cp.x, cp.y, cp.z, cp.w }, tc[4] = { cc.x, cc.y, cc.z, cc.w };
 #pragma unroll
-        for (int r = 0; r < BP_R; r++) {
-            const float x = s_x[idx + r * BP_THREADS];
-            ap[r] = fadd(ap[r], fmul(cp, x));
-            ac[r] = fadd(ac[r], fmul(cc, x));
-        }
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+            for (int i = 0; i < BP_R; i++) {
+                const float x = xs[4 + i - t];
+                ap[i] = fadd(ap[i], fmul(tp[t], x));
+                ac[i] = fadd(ac[i], fmul(tc[t], x));
+            }
+    };
+    const float4 *pq = reinterpret_cast<const float4 *>(s_p);
+    const float4 *cq = reinterpret_cast<const float4 *>(s_c);
+    int q = 3;                                   // next quad to bring in
+    for (int k = 0; k < Tpad; k += BP_UNROLL) {
+        group4(w0, w1, w2, pq[k >> 2], cq[k >> 2]);
+        w0 = quad(q++);                          // x[m-8 .. m-5] of the next group's m: the new "lo"
+        group4(w1, w2, w0, pq[(k >> 2) + 1], cq[(k >> 2) + 1]);
+        w1 = quad(q++);
+        group4(w2, w0, w1, pq[(k >> 2) + 2], cq[(k >> 2) + 2]);
+        w2 = quad(q++);
     }
     float *pilot = a.pilot + (size_t)c * a.pilot_stride;
     float *chan = a.chan + (size_t)c * a.if_stride + a.if_off;
+    const int n = n0 + BP_R * tid;
+    if (n + BP_R <= a.n_if && ((reinterpret_cast<uintptr_t>(pilot + n) | reinterpret_cast<uintptr_t>(chan + n)) & 15u) == 0) {
+        reinterpret_cast<float4 *>(pilot + n)[0] = make_float4(ap[0], ap[1], ap[2], ap[3]);
+        reinterpret_cast<float4 *>(pilot + n)[1] = make_float4(ap[4], ap[5], ap[6], ap[7]);
+        reinterpret_cast<float4 *>(chan + n)[0] = make_float4(ac[0], ac[1], ac[2], ac[3]);
+        reinterpret_cast<float4 *>(chan + n)[1] = make_float4(ac[4], ac[5], ac[6], ac[7]);
+    } else {
 #pragma unroll
-    for (int r = 0; r < BP_R; r++) {
-        const int n = n0 + tid + r * BP_THREADS;
-        if (n < a.n_if) {
-            pilot[n] = ap[r];
-            chan[n] = ac[r];
-        }
+        for (int i = 0; i < BP_R; i++)
+            if (n + i < a.n_if) {
+                pilot[n + i] = ap[i];
+                chan[n + i] = ac[i];
+            }
     }
 }
 
 cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStream_t s)
 {
-    const size_t smem = sizeof(float) * ((size_t)BP_TILE + 3 * a.T);
+    if (a.if_off < bp_front(a.T))                // the padded taps read this far in front of the chunk
+        return cudaErrorInvalidValue;
     dim3 grid((a.n_if + BP_TILE - 1) / BP_TILE, n_captures);
-    k_bandpass_pair<<<grid, BP_THREADS, smem, s>>>(a);
+    k_bandpass_pair<<<grid, BP_THREADS, bp_smem_bytes(a.T), s>>>(a);
     return cudaGetLastError();
 }
 
@@ -1096,8 +1152,12 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     int prof_n_tie = 0, prof_n_range = 0, prof_n_inv = 0;
     int prof_one_steps = 0, prof_one_groups = 0, prof_one_exact = 0, prof_one_short = 0, prof_checked = 0;
     __shared__ int s_prof[8];        // candidate warps: why a table was not emitted
-    if (threadIdx.x < 8)
+    __shared__ long long s_prof1[8]; // one-hypothesis groups: [0] predictor cycles waiting for warp 0, [1] predictor cycles stepping, [2] predictor blocks
+                                     // redone with the reduction, [3] candidate pass cycles (warp 2), [4] passes, [5] candidate cycles waiting for records
+    if (threadIdx.x < 8) {
         s_prof[threadIdx.x] = 0;
+        s_prof1[threadIdx.x] = 0;
+    }
 #endif
     if (warp == 0) {
         ch.integ = st[0];
@@ -1531,6 +1591,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const int u = live ? ub + lane : end - 1;
                     const int last = min(ub + PLL_BATCH1 - 1, end - 1);
                     int prog = 0, spin = 0;
+#ifdef FMRX_PLL_PROFILE
+                    const long long cw0 = clock64();
+#endif
                     for (;; spin++) {
                         const int seq = ld_v2(&s_ph[last & (PLL_PH_RING - 1)]).y;
                         if (seq == last + 1 || spin >= PLL_SPIN_LIMIT)
@@ -1544,6 +1607,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                         s_flag[1] = 1;
                         break;
                     }
+#ifdef FMRX_PLL_PROFILE
+                    const long long cw1 = clock64();
+#endif
                     const int2 cur = ld_v2(&s_ph[u & (PLL_PH_RING - 1)]);
                     bool ok = cur.y == u + 1;
                     double tad = s_hdr_tad;
@@ -1569,6 +1635,13 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     if (live)
                         st_v4(reinterpret_cast<PllRow1 *>(&s_tab[0]) + (u & (PLL_TABLES1 - 1)), __float_as_int(p_fmulf(k.kp, ed)),
                               __float_as_int(p_fmulf(k.ki, ed)), cur.x, ok ? u + 1 : -(u + 1));
+#ifdef FMRX_PLL_PROFILE
+                    if (lane == 0 && blockIdx.x == 0 && cand_id == 0) {
+                        s_prof1[3] += clock64() - cw1;
+                        s_prof1[4] += 1;
+                        s_prof1[5] += cw1 - cw0;
+                    }
+#endif
                 }
             }
         } else if (warp == PLL_PRED_WARP) {
@@ -1632,9 +1705,17 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 for (int t = 0; t < cnt; t += 8) {
                     const int u0 = base + t;
                     int spin = 0;                // stay within PLL_LEAD1 of warp 0
+#ifdef FMRX_PLL_PROFILE
+                    const long long pw0 = clock64();
+#endif
                     do {
                         asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(prog) : "r"(prog_a) : "memory");
                     } while (prog != PLL_ABANDONED && u0 - prog > PLL_LEAD1 - 8 && ++spin < PLL_SPIN_LIMIT);
+#ifdef FMRX_PLL_PROFILE
+                    const long long pw1 = clock64();
+                    if (lane == 0 && blockIdx.x == 0)
+                        s_prof1[0] += pw1 - pw0;
+#endif
                     if (prog == PLL_ABANDONED || spin >= PLL_SPIN_LIMIT)
                         break;
                     const unsigned h_a0 = h_a + (unsigned)(u0 & (PLL_RING - 1)) * (unsigned)sizeof(PllIn);
@@ -1684,6 +1765,12 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                         asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(ph_a0 + (unsigned)j * 8u), "r"(__float_as_int(phs[j])),
                                      "r"(u0 + j + 1)
                                      : "memory");
+#ifdef FMRX_PLL_PROFILE
+                    if (lane == 0 && blockIdx.x == 0) {
+                        s_prof1[1] += clock64() - pw1;
+                        s_prof1[2] += reduce;
+                    }
+#endif
                 }
             }
         } else if (role == 1 && io_id < PLL_IO_WARPS) {
@@ -1745,8 +1832,10 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                    (double)prof_pre / n_groups, (double)prof_wait / n_groups, (double)prof_steps_cyc / n_groups,
                    (double)(clock64() - prof_k0 - prof_pre - prof_wait - prof_steps_cyc) / n_groups);
         if (c == 0)
-            printf("pll dbg one-hypothesis: groups %d (cut short %d), %.1f cyc/step over %d steps, exact blocks %d | groups without tables %d\n",
-                   prof_one_groups, prof_one_short, prof_one_steps ? (double)prof_one_cyc / prof_one_steps : 0.0, prof_one_steps, prof_one_exact, prof_checked);
+            printf("pll dbg one-hypothesis: groups %d (cut short %d), %.1f cyc/step over %d steps, exact blocks %d | groups without tables %d | predictor: %.1f cyc/step stepping, %.1f waiting for warp 0, %lld blocks of 8 reduced | candidate warp 2: %lld passes, %.0f cyc each, %.0f waiting for records\n",
+                   prof_one_groups, prof_one_short, prof_one_steps ? (double)prof_one_cyc / prof_one_steps : 0.0, prof_one_steps, prof_one_exact, prof_checked,
+                   prof_one_steps ? (double)s_prof1[1] / prof_one_steps : 0.0, prof_one_steps ? (double)s_prof1[0] / prof_one_steps : 0.0, s_prof1[2],
+                   s_prof1[4], s_prof1[4] ? (double)s_prof1[3] / s_prof1[4] : 0.0, s_prof1[4] ? (double)s_prof1[5] / s_prof1[4] : 0.0);
 #endif
         st[6] = (float)(n_groups + 1000 * min(n_exact, 999));     // diagnostics of the last launch
         st[7] = s_flag[1] ? -1.0f : (float)n_redone;
@@ -1826,6 +1915,7 @@ __global__ void __launch_bounds__(kAudioTile) k_audio(const AudioArgs a, const i
     float *s_mix = s_dem + span;             // [span]
     float *s_tail = s_mix + span;            // [T]   demod[B-(T-1) .. B)
     float *s_mono = s_tail + T;              // [kAudioTile + kMonoDelay]
+    float *s_cf = s_mono + kAudioTile + kMonoDelay;   // [T] the taps, when every frame has the same phase (U == 1: modes 0, 1)
 
     const int c = blockIdx.y, tid = threadIdx.x;
     const int tiles_per_block = NA / kAudioTile;
@@ -1869,6 +1959,9 @@ __global__ void __launch_bounds__(kAudioTile) k_audio(const AudioArgs a, const i
     if (need_tail)
         for (int i = tid; i < T - 1; i += kAudioTile)
             s_tail[i] = demod[blk0 + B - (T - 1) + i];
+    if (U == 1)
+        for (int i = tid; i < T; i += kAudioTile)
+            s_cf[i] = a.coef_pm[i];
     __syncthreads();
 
     // this thread's frame
@@ -1877,22 +1970,20 @@ __global__ void __launch_bounds__(kAudioTile) k_audio(const AudioArgs a, const i
     {
         const int nd = n * D;
         const int q = nd / U;
-        const float *cf = a.coef_pm + (size_t)(nd % U) * T;
-        for (int t = 0; t < T; t++) {
-            const int r = q - t;
+        const float *cf = U == 1 ? s_cf : a.coef_pm + (size_t)(nd % U) * T;
+        // taps 0..q reach samples of this block (r >= 0); only the first frames of a block go on into the quirk:
+        // mono takes the previous block's MIXER tail, stereo this block's DEMOD tail (src/project.cpp:114,146,172)
+        const int t_in = min(T, q + 1);
+        const float *xd = s_dem + (q - r_min), *xm = s_mix + (q - r_min);
+        for (int t = 0; t < t_in; t++) {
             const float cv = cf[t];
-            const float xd = s_dem[r - r_min];
-            const float xm = s_mix[r - r_min];
-            float x_mono, x_st;
-            if (r >= 0) {
-                x_mono = xd;
-                x_st = xm;
-            } else {
-                x_mono = xm;                       // previous block's mixer tail
-                x_st = s_tail[T - 1 + r];          // this block's demod tail
-            }
-            am = fadd(am, fmul(cv, x_mono));
-            as = fadd(as, fmul(cv, x_st));
+            am = fadd(am, fmul(cv, xd[-t]));
+            as = fadd(as, fmul(cv, xm[-t]));
+        }
+        for (int t = t_in; t < T; t++) {
+            const float cv = cf[t];
+            am = fadd(am, fmul(cv, xm[-t]));
+            as = fadd(as, fmul(cv, s_tail[T - 1 + q - t]));
         }
     }
     s_mono[tid + kMonoDelay] = am;
@@ -1938,7 +2029,7 @@ static inline int audio_span(int T, int U, int D)
 
 int audio_smem_bytes(int T, int U, int D)
 {
-    return (int)sizeof(float) * (2 * audio_span(T, U, D) + T + kAudioTile + kMonoDelay);
+    return (int)sizeof(float) * (2 * audio_span(T, U, D) + 2 * T + kAudioTile + kMonoDelay);
 }
 
 cudaError_t launch_audio(const AudioArgs &a, int n_captures, cudaStream_t s)

@@ -50,10 +50,48 @@ def test_unmodified_reference_main_links_against_the_shim(fm, port, synth):
         pytest.skip("oracle/_ref/project_dropin not built (needs the reference checkout at build time)")
     info = port.mode(0, 51)
     iq = synth.synth_iq(40 * info.block_size // 2, info.rf_fs, seed=77)
+    import json, time
+    t0 = time.perf_counter()
     r = _run(DROPIN, ["0", "2"], iq.tobytes(), timeout=600)
+    w_short = time.perf_counter() - t0
     assert r.returncode == 1 and b"End of input stream reached!" in r.stderr
+    # how fast the level-1 drop-in is (eleven operator calls per block, each with its own copies): the marginal
+    # time per block between a 40- and a 400-block run (process start and context creation cancel).  Recorded, not a gate.
+    long_iq = np.tile(iq, 10)
+    t0 = time.perf_counter()
+    r2 = _run(DROPIN, ["0", "2"], long_iq.tobytes(), timeout=600)
+    w_long = time.perf_counter() - t0
+    assert r2.returncode == 1
+    block_s = info.block_size / 2 / info.rf_fs
+    rec = {"what": "unmodified reference main + filter.h shim + libfmrx_b200 (operator entry points), mode 0, 51 taps",
+           "wall_40_blocks_s": w_short, "wall_400_blocks_s": w_long, "ms_per_block": 1e3 * (w_long - w_short) / 360,
+           "real_time_factor": 360 * block_s / max(1e-9, w_long - w_short)}
+    print(rec)
+    out_dir = ROOT / "gpurun_out"
+    if out_dir.is_dir():
+        (out_dir / "dropin_rtf.json").write_text(json.dumps(rec) + "\n")
     out = np.frombuffer(r.stdout, np.int16)
     ref, _ = port.chain(0, 51).run(iq)
     per_block = 2 * info.audio_per_block
     assert len(out) % per_block == 0 and 0 <= len(ref) - len(out) <= 4 * per_block and len(out) > 20 * per_block
     assert np.array_equal(out, ref[:len(out)])
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_cli_streaming_stats_and_latency(fm, port, synth, mode):
+    """The live path (src/project.cpp:392-393: rtl_sdr | project | aplay): default ~0.2 s chunks through the
+    reader / process / writer ring.  PCM identical to the oracle; --stats reports a sustained real-time factor
+    above 1 (it must keep up with a live dongle) and a per-chunk latency."""
+    import json
+    info = port.mode(mode, 51)
+    nb = max(3, int(3.0 * info.rf_fs * 2 / info.block_size))
+    iq = synth.synth_iq_exact(nb * info.block_size // 2, float(info.rf_fs), station=mode)
+    r = _run(CLI, [str(mode), "s", "--stats"], iq.tobytes())
+    assert r.returncode == 1
+    ref, _ = port.chain(mode, 51).run(iq)
+    assert np.array_equal(np.frombuffer(r.stdout, np.int16), ref)
+    line = [ln for ln in r.stderr.decode().splitlines() if ln.startswith("fmrx stats: ")]
+    assert line, r.stderr.decode()
+    st = json.loads(line[0][len("fmrx stats: "):])
+    print(st)
+    assert st["real_time_factor"] > 1.0 and st["latency_ms"]["max"] > 0
