@@ -97,6 +97,28 @@ def main():
             "gpu_launches": launches, "trigOffset_end": float(st[5]),
             "parity_whole_run": f"{same}/{C} captures bit-identical to the reference PCM (sha256 over {nb * 2 * info.audio_per_block} int16 each)",
         }), flush=True)
+        if name == "m0_t301_1hour":
+            # the same capture time-sharded (fmrx_long_*: feed-forward stages of all shards at once from FIR halos, the
+            # PLL state handed from shard to shard, PCM gathered on the first device) over every visible GPU -- two
+            # shards on the one GPU if there is only one
+            n_dev = torch.cuda.device_count()
+            devs = list(range(n_dev)) if n_dev > 1 else [0, 0]
+            with fm.LongCapture(mode, taps, devs, nb) as lc:
+                ptrs, keep = [], []
+                for r, d in enumerate(devs):
+                    first, cnt, halo = lc.shard(r)
+                    piece = iq[0, (first - halo) * info.block_size:(first + cnt) * info.block_size]
+                    t = piece if d == 0 else piece.to(f"cuda:{d}")
+                    keep.append(t)
+                    ptrs.append(t.data_ptr())
+                pcm.zero_()
+                torch.cuda.synchronize()
+                ms_l = lc.process_device(ptrs, pcm.data_ptr())
+                ok = hashlib.sha256(pcm[0].cpu().numpy().tobytes()).hexdigest() == g0["pcm_sha256"]
+            print(json.dumps({"config": name + "_time_sharded", "what": f"the same capture as {len(devs)} time shards on devices {devs}",
+                              "iq_msps": n_pairs / (ms_l * 1e-3) / 1e6, "ms": ms_l, "single_pipeline_ms": ms,
+                              "parity_whole_run": "bit-identical to the reference PCM (sha256)" if ok else "MISMATCH"}), flush=True)
+            del keep
         del iq, pcm
         torch.cuda.empty_cache()
 
