@@ -467,12 +467,12 @@ int create_impl(fmrx_pipeline *p, const fmrx_config *cfg)
         return FMRX_ERR_ARG;
     int cb = static_cast<int>(std::min<long long>(cfg->chunk_blocks, cb_max));
     if (cb <= 0) {
-        // aim at ~128 MiB per IF-rate array per chunk: a K3 launch has to wait for whole SMs to drain
+        // aim at ~256 MiB per IF-rate array per chunk: a K3 launch has to wait for whole SMs to drain
         // of the FIR CTAs of the neighbouring chunks (its CTAs claim a whole SM each), a third of a
-        // millisecond that is 12 % of a launch at 32 MiB and 3 % at 128
-        const size_t target_if = (128u << 20) / sizeof(float) / C;
+        // millisecond that is 12 % of a launch at 32 MiB, 3 % at 128 and 1.5 % at 256
+        const size_t target_if = (256u << 20) / sizeof(float) / C;
         cb = static_cast<int>(std::max<size_t>(1, target_if / mi.if_per_block));
-        cb = static_cast<int>(std::min<long long>(std::min(cb, 4096), cb_max));
+        cb = static_cast<int>(std::min<long long>(std::min(cb, 8192), cb_max));
     }
     p->ramp = cfg->chunk_blocks <= 0;
     p->chunk_blocks = cb;

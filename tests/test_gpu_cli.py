@@ -56,16 +56,16 @@ def test_unmodified_reference_main_links_against_the_shim(fm, port, synth):
     w_short = time.perf_counter() - t0
     assert r.returncode == 1 and b"End of input stream reached!" in r.stderr
     # how fast the level-1 drop-in is (eleven operator calls per block, each with its own copies): the marginal
-    # time per block between a 40- and a 400-block run (process start and context creation cancel).  Recorded, not a gate.
-    long_iq = np.tile(iq, 10)
+    # time per block between a 40- and a 2000-block run (process start and context creation cancel).  Recorded, not a gate.
+    long_iq = np.tile(iq, 50)
     t0 = time.perf_counter()
     r2 = _run(DROPIN, ["0", "2"], long_iq.tobytes(), timeout=600)
     w_long = time.perf_counter() - t0
     assert r2.returncode == 1
     block_s = info.block_size / 2 / info.rf_fs
     rec = {"what": "unmodified reference main + filter.h shim + libfmrx_b200 (operator entry points), mode 0, 51 taps",
-           "wall_40_blocks_s": w_short, "wall_400_blocks_s": w_long, "ms_per_block": 1e3 * (w_long - w_short) / 360,
-           "real_time_factor": 360 * block_s / max(1e-9, w_long - w_short)}
+           "wall_40_blocks_s": w_short, "wall_2000_blocks_s": w_long, "ms_per_block": 1e3 * (w_long - w_short) / 1960,
+           "real_time_factor": 1960 * block_s / max(1e-9, w_long - w_short)}
     print(rec)
     out_dir = ROOT / "gpurun_out"
     if out_dir.is_dir():
