@@ -237,6 +237,25 @@ int fmrx_long_last_ms(const fmrx_long_capture *h, float *ms);
 /* The six PLL scalars after the last shard (fmrx_pll's order). */
 int fmrx_long_pll_state(fmrx_long_capture *h, float out[6]);
 
+/* ---------------------------------------------------------------------- */
+/* The reference's RDS sketch, src/project.cpp:200-271 (rds_thread: compiled */
+/* into the reference, never started): 54-60 kHz channel band-pass, squarer, */
+/* 113.5-114.5 kHz band-pass, PLL(114000, bp_fs, 0.5, 0, 0.01), the channel   */
+/* delayed by channel_delay samples, mixer.  One call = one block of          */
+/* demodulated samples (FMRX_STAGE_DEMOD); states carry across calls.         */
+/* ---------------------------------------------------------------------- */
+typedef struct fmrx_rds fmrx_rds;
+int fmrx_rds_create(fmrx_rds **out, float bp_fs, int taps, int channel_delay, int device);
+int fmrx_rds_destroy(fmrx_rds *h);
+int fmrx_rds_reset(fmrx_rds *h);
+/* HOST pointers.  demod: n samples, n >= taps-1 and n >= channel_delay (what the
+ * reference's own code needs).  mixer_out receives mixer_data (:269);
+ * channel_out / carrier_out (optional, may be NULL) the extracted channel
+ * (:244) and the band-passed squared carrier (:254). */
+int fmrx_rds_process(fmrx_rds *h, const float *demod, size_t n, float *mixer_out,
+                     float *channel_out, float *carrier_out);
+int fmrx_rds_pll_state(fmrx_rds *h, float out[6]);
+
 #ifdef __cplusplus
 }
 #endif

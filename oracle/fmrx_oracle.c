@@ -451,3 +451,72 @@ void orc_chain_set_state(orc_chain *c, const float *in)
     memcpy(c->st_audio, in, ta * 4); in += ta;
     memcpy(c->mono_state, in, ORC_MONO_DELAY * 4);
 }
+
+/* ---- RDS front end, as far as the reference sketches it (src/project.cpp:200-271) -------
+ * rds_thread is compiled into the reference but never started (its queue pushes are
+ * commented out, :72-83): channel extraction 54-60 kHz, squarer, 113.5-114.5 kHz band-pass,
+ * PLL(114000, bp_fs, 0.5, 0, 0.01), a delay of channel_delay samples on the channel, mixer.
+ * Restated block by block with the operators above; every stage carries its state. */
+struct orc_rds {
+    int taps, delay;
+    float fs;
+    float *extract_coeff, *carrier_coeff;    /* :210, :217 */
+    float *channel_state, *carrier_state;    /* :209, :216  (taps-1 each, zero) */
+    float *shift_state;                      /* :207  channel_delay zeros */
+    float pll[6];                            /* :219-224 */
+};
+
+orc_rds *orc_rds_create(float bp_fs, int taps, int channel_delay)
+{
+    if (taps < 2 || channel_delay < 0)
+        return NULL;
+    orc_rds *r = (orc_rds *)calloc(1, sizeof(*r));
+    r->taps = taps;
+    r->delay = channel_delay;
+    r->fs = bp_fs;
+    r->extract_coeff = (float *)calloc(taps, sizeof(float));
+    r->carrier_coeff = (float *)calloc(taps, sizeof(float));
+    r->channel_state = (float *)calloc(taps - 1, sizeof(float));
+    r->carrier_state = (float *)calloc(taps - 1, sizeof(float));
+    r->shift_state = (float *)calloc(channel_delay ? channel_delay : 1, sizeof(float));
+    orc_bpf_taps(r->extract_coeff, bp_fs, 54000.0f, 60000.0f, taps);          /* :210 */
+    orc_bpf_taps(r->carrier_coeff, bp_fs, 113500.0f, 114500.0f, taps);        /* :217 */
+    r->pll[0] = 0.0f; r->pll[1] = 0.0f; r->pll[2] = 1.0f; r->pll[3] = 0.0f;   /* :219-224 */
+    r->pll[4] = 1.0f; r->pll[5] = 0.0f;
+    return r;
+}
+
+void orc_rds_destroy(orc_rds *r)
+{
+    if (!r)
+        return;
+    free(r->extract_coeff); free(r->carrier_coeff); free(r->channel_state);
+    free(r->carrier_state); free(r->shift_state); free(r);
+}
+
+/* One block of demod (n >= taps-1 and n >= channel_delay, as the reference's own code needs)
+ * -> mixer_data (:269).  channel / carrier (optional) receive the intermediate stages. */
+void orc_rds_block(orc_rds *r, const float *demod, int n, float *mixer_out, float *channel, float *carrier_nco)
+{
+    float *chan = (float *)malloc(sizeof(float) * n);
+    float *sq = (float *)malloc(sizeof(float) * n);
+    float *car = (float *)malloc(sizeof(float) * n);
+    float *shift = (float *)malloc(sizeof(float) * n);
+    orc_resample(chan, r->channel_state, r->taps - 1, demod, n, r->extract_coeff, r->taps, 1, 1);   /* :244 */
+    for (int i = 0; i < n; i++)
+        sq[i] = chan[i] * chan[i];                                                                 /* :249-251 */
+    orc_resample(car, r->carrier_state, r->taps - 1, sq, n, r->carrier_coeff, r->taps, 1, 1);       /* :254 */
+    orc_pll(car, n, 114000.0f, r->fs, 0.5f, 0.0f, 0.01f, r->pll, NULL);                           /* :256 */
+    for (int i = 0; i < r->delay; i++)                                                            /* :259-266 */
+        shift[i] = r->shift_state[i];
+    for (int i = r->delay; i < n; i++)
+        shift[i] = chan[i - r->delay];
+    for (int i = 0; i < r->delay; i++)
+        r->shift_state[i] = chan[n - r->delay + i];
+    orc_mixer(mixer_out, car, shift, n);                                                          /* :269 */
+    if (channel)
+        memcpy(channel, chan, sizeof(float) * n);
+    if (carrier_nco)
+        memcpy(carrier_nco, car, sizeof(float) * n);
+    free(chan); free(sq); free(car); free(shift);
+}

@@ -57,6 +57,12 @@ void orc_lr_extract(float *left, float *right, const float *mono,
 /* src/project.cpp:179-193: R first, truncation, NaN -> 0 */
 void orc_pcm_pack(int16_t *pcm, const float *left, const float *right, int n);
 
+/* ---- RDS front end as far as the reference sketches it (src/project.cpp:200-271) ---- */
+typedef struct orc_rds orc_rds;
+orc_rds *orc_rds_create(float bp_fs, int taps, int channel_delay);
+void orc_rds_destroy(orc_rds *r);
+void orc_rds_block(orc_rds *r, const float *demod, int n, float *mixer_out, float *channel, float *carrier_nco);
+
 /* ---- mode table (src/project.cpp:304-364) ------------------------------ */
 typedef struct {
     int mode;

@@ -322,3 +322,33 @@ class Reference(_OpsMixin):
         name = "project" if taps == 51 else f"project_t{taps}"
         p = HERE / "_ref" / name
         return p if p.exists() else None
+
+
+class RdsSketch:
+    """The reference's RDS sketch (src/project.cpp:200-271), block by block: ``impl`` is a Port (the C
+    restatement) or a Reference (the reference's own operators in rds_thread's call order)."""
+
+    def __init__(self, impl, bp_fs: float = 240e3, taps: int = 51, channel_delay: int = 5):
+        self.lib = impl.lib
+        self.pfx = "ref_" if isinstance(impl, Reference) else "orc_"
+        create = getattr(self.lib, self.pfx + "rds_create")
+        create.restype = C.c_void_p
+        create.argtypes = [C.c_float, C.c_int, C.c_int]
+        self.block_fn = getattr(self.lib, self.pfx + "rds_block")
+        self.block_fn.restype = None
+        self.block_fn.argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, _f32p, _f32p]
+        self.destroy = getattr(self.lib, self.pfx + "rds_destroy")
+        self.destroy.argtypes = [C.c_void_p]
+        self.h = create(bp_fs, taps, channel_delay)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.destroy(self.h)
+            self.h = None
+
+    def block(self, demod):
+        """-> (mixer_data, channel_data, carrier_data after the PLL = its NCO output)"""
+        demod = np.ascontiguousarray(demod, np.float32)
+        out, chan, nco = (np.zeros(len(demod), np.float32) for _ in range(3))
+        self.block_fn(self.h, _fp(demod), len(demod), _fp(out), _fp(chan), _fp(nco))
+        return out, chan, nco

@@ -193,4 +193,50 @@ void ref_chain_get_pll(const ref_chain *c, float *st)
     st[4] = c->nco_state; st[5] = c->trig_off;
 }
 
+
+/* ---- the reference's RDS sketch (src/project.cpp:200-271), replayed with the reference's OWN
+ * operators in the order rds_thread calls them (the thread itself is never started and sits
+ * in the same translation unit as main, so it cannot be linked from here) ---- */
+struct ref_rds {
+    float fs;
+    int taps, delay;
+    vf extract_coeff, carrier_coeff, channel_state, carrier_state, shift_state;
+    float integ, phase, fb_i, fb_q, nco_state, trig_off;
+};
+
+ref_rds *ref_rds_create(float bp_fs, int taps, int channel_delay)
+{
+    ref_rds *r = new ref_rds();
+    r->fs = bp_fs;
+    r->taps = taps;
+    r->delay = channel_delay;
+    r->channel_state.assign(taps - 1, 0.0);                                      /* :209 */
+    r->carrier_state.assign(taps - 1, 0.0);                                      /* :216 */
+    r->shift_state.assign(channel_delay, 0.0);                                   /* :207 */
+    impulseResponseBPF(r->extract_coeff, bp_fs, 54000, 60000, taps);             /* :210 */
+    impulseResponseBPF(r->carrier_coeff, bp_fs, 113500, 114500, taps);           /* :217 */
+    r->integ = 0.0; r->phase = 0.0; r->fb_i = 1.0; r->fb_q = 0.0; r->trig_off = 0.0; r->nco_state = 1.0;   /* :219-224 */
+    return r;
+}
+
+void ref_rds_destroy(ref_rds *r) { delete r; }
+
+void ref_rds_block(ref_rds *r, const float *demod, int n, float *mixer_out, float *channel, float *carrier_nco)
+{
+    vf demod_data(demod, demod + n), channel_data, channel_squared, carrier_data, channel_shift, mixer_data;
+    resample(channel_data, r->channel_state, demod_data, r->extract_coeff, 1, 1);                  /* :244 */
+    channel_squared.resize(channel_data.size(), 0.0);
+    for (size_t i = 0; i < channel_data.size(); i++)
+        channel_squared[i] = channel_data[i] * channel_data[i];                                    /* :249-251 */
+    resample(carrier_data, r->carrier_state, channel_squared, r->carrier_coeff, 1, 1);             /* :254 */
+    PLL(carrier_data, 114000, r->fs, 0.5, 0, 0.01, r->integ, r->phase, r->fb_i, r->fb_q, r->nco_state, r->trig_off);   /* :256 */
+    channel_shift.insert(channel_shift.end(), r->shift_state.begin(), r->shift_state.end());       /* :259-263 */
+    channel_shift.insert(channel_shift.end(), channel_data.begin(), channel_data.end() - r->delay);
+    r->shift_state.assign(channel_data.end() - r->delay, channel_data.end());                      /* :265-266 */
+    mixer(mixer_data, carrier_data, channel_shift);                                                /* :269 */
+    out_copy(mixer_out, mixer_data);
+    if (channel) out_copy(channel, channel_data);
+    if (carrier_nco) out_copy(carrier_nco, carrier_data);
+}
+
 } /* extern "C" */

@@ -41,6 +41,7 @@ ABI_SYMBOLS = (
     "fmrx_last_timing",
     "fmrx_long_create", "fmrx_long_destroy", "fmrx_long_shard", "fmrx_long_process", "fmrx_long_process_device",
     "fmrx_long_last_ms", "fmrx_long_pll_state",
+    "fmrx_rds_create", "fmrx_rds_destroy", "fmrx_rds_reset", "fmrx_rds_process", "fmrx_rds_pll_state",
 )
 
 
@@ -119,6 +120,11 @@ def load() -> C.CDLL:
     L.fmrx_long_process_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
     L.fmrx_long_last_ms.argtypes = [C.c_void_p, _f32p]
     L.fmrx_long_pll_state.argtypes = [C.c_void_p, _f32p]
+    L.fmrx_rds_create.argtypes = [C.POINTER(C.c_void_p), C.c_float, C.c_int, C.c_int, C.c_int]
+    L.fmrx_rds_destroy.argtypes = [C.c_void_p]
+    L.fmrx_rds_reset.argtypes = [C.c_void_p]
+    L.fmrx_rds_process.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, _f32p, _f32p]
+    L.fmrx_rds_pll_state.argtypes = [C.c_void_p, _f32p]
     L.fmrx_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.fmrx_last_timing.argtypes = [C.c_void_p, _f32p]
     _lib = L
@@ -387,4 +393,40 @@ class LongCapture:
     def pll_state(self) -> np.ndarray:
         st = np.zeros(6, np.float32)
         _check(self._L.fmrx_long_pll_state(self._h, _fp(st)), "fmrx_long_pll_state")
+        return st
+
+
+class RdsFront:
+    """The reference's RDS sketch (src/project.cpp:200-271) on the device: ``process(demod_block)`` returns
+    (mixer_data, channel_data, carrier_data) of one block; states carry across calls."""
+
+    def __init__(self, bp_fs: float = 240e3, taps: int = 51, channel_delay: int = 5, device: int = -1):
+        self._L = load()
+        h = C.c_void_p()
+        _check(self._L.fmrx_rds_create(C.byref(h), bp_fs, taps, channel_delay, device), "fmrx_rds_create")
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._L.fmrx_rds_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self):
+        _check(self._L.fmrx_rds_reset(self._h), "fmrx_rds_reset")
+
+    def process(self, demod: np.ndarray):
+        demod = np.ascontiguousarray(demod, np.float32)
+        out, chan, car = (np.zeros(len(demod), np.float32) for _ in range(3))
+        _check(self._L.fmrx_rds_process(self._h, _fp(demod), len(demod), _fp(out), _fp(chan), _fp(car)), "fmrx_rds_process")
+        return out, chan, car
+
+    def pll_state(self) -> np.ndarray:
+        st = np.zeros(6, np.float32)
+        _check(self._L.fmrx_rds_pll_state(self._h, _fp(st)), "fmrx_rds_pll_state")
         return st

@@ -1350,3 +1350,163 @@ extern "C" int fmrx_long_pll_state(fmrx_long_capture *L, float out[6])
         return FMRX_ERR_ARG;
     return fmrx_get_pll_state(L->pipe[L->n - 1], 0, out);
 }
+
+// ---------------------------------------------------------------------------
+// The reference's RDS sketch (src/project.cpp:200-271)
+// ---------------------------------------------------------------------------
+// rds_thread is compiled into the reference but never started: channel extraction (54-60 kHz band-pass of the
+// demodulated FM), squarer, 113.5-114.5 kHz band-pass, PLL(114000, bp_fs, 0.5, 0, 0.01), a delay of channel_delay
+// samples on the channel, mixer -- and there the sketch ends (the 3 kHz low-pass is designed, :231, never applied).
+// The same steps on the device, per call = per block of demodulated samples, with the carried states of
+// :207-224 in device memory: the operator FIR kernel (k_resample), k_pll unchanged with the sketch's parameters,
+// and two element-wise kernels.
+struct fmrx_rds {
+    int device = 0, taps = 0, delay = 0;
+    float fs = 0;
+    PllParams prm{};
+    float *d_extract = nullptr, *d_carrier = nullptr;         // taps
+    float *d_chan_state = nullptr, *d_car_state = nullptr;    // taps-1
+    float *d_shift_state = nullptr;                           // delay
+    float *d_pll_state = nullptr;                             // 8
+    float *d_buf = nullptr;                                   // 6 arrays of cap floats: demod, chan, sq, car, trig, out
+    size_t cap = 0;
+};
+
+namespace {
+void free_rds(fmrx_rds *r)
+{
+    if (!r)
+        return;
+    cudaSetDevice(r->device);
+    cudaDeviceSynchronize();
+    for (float *q : { r->d_extract, r->d_carrier, r->d_chan_state, r->d_car_state, r->d_shift_state, r->d_pll_state, r->d_buf })
+        if (q)
+            cudaFree(q);
+    delete r;
+}
+
+int rds_reset_state(fmrx_rds *r)
+{
+    CU(cudaMemset(r->d_chan_state, 0, (r->taps - 1) * sizeof(float)));      // :209
+    CU(cudaMemset(r->d_car_state, 0, (r->taps - 1) * sizeof(float)));       // :216
+    CU(cudaMemset(r->d_shift_state, 0, std::max(1, r->delay) * sizeof(float)));   // :207
+    const float st[8] = { 0.0f, 0.0f, 1.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f };     // :219-224
+    CU(cudaMemcpy(r->d_pll_state, st, sizeof(st), cudaMemcpyHostToDevice));
+    return FMRX_OK;
+}
+}  // namespace
+
+extern "C" int fmrx_rds_create(fmrx_rds **out, float bp_fs, int taps, int channel_delay, int device)
+{
+    if (!out || taps < 2 || taps > kMaxTaps || channel_delay < 0 || !(bp_fs > 0))
+        return FMRX_ERR_ARG;
+    *out = nullptr;
+    if (fmrx_device_count() < 1) {
+        std::snprintf(g_err, sizeof(g_err), "no CUDA device");
+        return FMRX_ERR_NO_DEVICE;
+    }
+    if (device < 0)
+        CU(cudaGetDevice(&device));
+    CU(cudaSetDevice(device));
+    fmrx_rds *r = new (std::nothrow) fmrx_rds();
+    if (!r)
+        return FMRX_ERR_ALLOC;
+    r->device = device;
+    r->taps = taps;
+    r->delay = channel_delay;
+    r->fs = bp_fs;
+    r->prm = make_pll_params(114000.0f, bp_fs, 0.5f, 0.0f, 0.01f);              // :256
+    std::vector<float> ex(taps), ca(taps);
+    fmrx_impulse_response_bpf(ex.data(), bp_fs, 54000.0f, 60000.0f, taps);      // :210
+    fmrx_impulse_response_bpf(ca.data(), bp_fs, 113500.0f, 114500.0f, taps);    // :217
+    auto fail = [&](int rc) {
+        free_rds(r);
+        return rc;
+    };
+    if (dalloc(&r->d_extract, taps) != cudaSuccess || dalloc(&r->d_carrier, taps) != cudaSuccess ||
+        dalloc(&r->d_chan_state, taps - 1) != cudaSuccess || dalloc(&r->d_car_state, taps - 1) != cudaSuccess ||
+        dalloc(&r->d_shift_state, std::max(1, channel_delay)) != cudaSuccess || dalloc(&r->d_pll_state, 8) != cudaSuccess)
+        return fail(FMRX_ERR_ALLOC);
+    if (cudaMemcpy(r->d_extract, ex.data(), taps * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(r->d_carrier, ca.data(), taps * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(FMRX_ERR_CUDA);
+    const int rc = rds_reset_state(r);
+    if (rc != FMRX_OK)
+        return fail(rc);
+    *out = r;
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_rds_destroy(fmrx_rds *r)
+{
+    free_rds(r);
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_rds_reset(fmrx_rds *r)
+{
+    if (!r)
+        return FMRX_ERR_ARG;
+    CU(cudaSetDevice(r->device));
+    CU(cudaDeviceSynchronize());
+    return rds_reset_state(r);
+}
+
+extern "C" int fmrx_rds_process(fmrx_rds *r, const float *demod, size_t n, float *mixer_out, float *channel_out,
+                                float *carrier_out)
+{
+    if (!r || !demod || !mixer_out || n > 0x7fffffffu)
+        return FMRX_ERR_ARG;
+    // the reference's own code needs a block at least as long as its filters and its delay (:99-100, :263)
+    if (n < static_cast<size_t>(r->taps - 1) || n < static_cast<size_t>(r->delay))
+        return FMRX_ERR_ARG;
+    CU(cudaSetDevice(r->device));
+    if (n > r->cap) {
+        if (r->d_buf)
+            cudaFree(r->d_buf);
+        r->d_buf = nullptr;
+        r->cap = 0;
+        CU(dalloc(&r->d_buf, 6 * n));
+        r->cap = n;
+    }
+    float *d_demod = r->d_buf, *d_chan = d_demod + r->cap, *d_sq = d_chan + r->cap, *d_car = d_sq + r->cap,
+          *d_trig = d_car + r->cap, *d_out = d_trig + r->cap;
+    const int ni = static_cast<int>(n), T = r->taps;
+    const size_t t1 = static_cast<size_t>(T - 1) * sizeof(float);
+    CU(cudaMemcpy(d_demod, demod, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_resample(d_chan, ni, r->d_chan_state, T - 1, d_demod, ni, r->d_extract, T, 1, 1, 0));      // :244
+    CU(cudaMemcpyAsync(r->d_chan_state, d_demod + (n - (T - 1)), t1, cudaMemcpyDeviceToDevice, 0));      // filter.cpp:95-102
+    CU(launch_square(d_sq, d_chan, n, 0));                                                               // :249-251
+    CU(launch_resample(d_car, ni, r->d_car_state, T - 1, d_sq, ni, r->d_carrier, T, 1, 1, 0));           // :254
+    CU(cudaMemcpyAsync(r->d_car_state, d_sq + (n - (T - 1)), t1, cudaMemcpyDeviceToDevice, 0));
+    if (carrier_out)         // (the band-passed carrier, before the PLL overwrites it with its NCO output)
+        CU(cudaMemcpyAsync(carrier_out, d_car, n * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    PllArgs a{};
+    a.pilot = d_car;
+    a.pilot_stride = n;
+    a.trig = d_trig;
+    a.if_stride = n;
+    a.if_off = 0;
+    a.n_if = ni;
+    a.state = r->d_pll_state;
+    a.prm = r->prm;
+    CU(launch_pll(a, 1, 0));                                                                             // :256
+    CU(launch_rds_mix(d_out, d_trig, d_chan, r->d_shift_state, r->delay, n, r->prm.scale, r->prm.adjust, 0));   // :259-263, :269
+    if (r->delay)
+        CU(cudaMemcpyAsync(r->d_shift_state, d_chan + (n - r->delay), r->delay * sizeof(float), cudaMemcpyDeviceToDevice, 0));   // :265-266
+    CU(cudaMemcpy(mixer_out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (channel_out)
+        CU(cudaMemcpy(channel_out, d_chan, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return FMRX_OK;
+}
+
+extern "C" int fmrx_rds_pll_state(fmrx_rds *r, float out[6])
+{
+    if (!r || !out)
+        return FMRX_ERR_ARG;
+    CU(cudaSetDevice(r->device));
+    float st[8];
+    CU(cudaMemcpy(st, r->d_pll_state, sizeof(st), cudaMemcpyDeviceToHost));
+    std::memcpy(out, st, 6 * sizeof(float));
+    return FMRX_OK;
+}

@@ -98,4 +98,9 @@ cudaError_t launch_lr_extract(float *left, float *right, const float *mono, cons
 cudaError_t launch_pcm_pack(int16_t *pcm, const float *left, const float *right, size_t n,
                             cudaStream_t s);
 
+// the reference's RDS sketch (src/project.cpp:200-271)
+cudaError_t launch_square(float *out, const float *x, size_t n, cudaStream_t s);
+cudaError_t launch_rds_mix(float *out, const float *trig, const float *chan, const float *shift_state, int delay, size_t n,
+                           float scale, float adjust, cudaStream_t s);
+
 }  // namespace fmrx

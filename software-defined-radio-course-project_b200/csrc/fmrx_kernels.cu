@@ -60,82 +60,85 @@ static DeviceCfg *device_cfg()
 constexpr int RF_COMPUTED = 512;                        // IF outputs computed per tile
 constexpr int RF_REAL = RF_COMPUTED - 1;                // 511 demod samples per tile
 
-// ---- K1, register-window version (decimation known at compile time) ----------------
+// ---- K1: register delay line over the RAW u8 tile (decimation known at compile time) ----------------
 //
-// Output n, tap k reads x[n*D - k].  A thread owns R = 4 consecutive outputs n..n+3, and
-// output n+i at tap k reads exactly the sample output n read at tap k - i*D.  So only
-// output n ("i = 0") loads from shared memory, one sample per plane per tap, into a
-// circular register delay line of L = 3*D entries; outputs n+1..n+3 take theirs from the
-// line, D, 2D and 3D taps back.  The tap loop is unrolled over one trip round the line so
-// that every line index is static.  Per tap: 2 sample LDS + 1 broadcast tap LDS against
-// 8 FMUL + 8 FADD -- FP32-pipe bound instead of shared-memory bound.  Each accumulator still
-// sees its products in ascending tap order.  T is padded to a multiple of L with zero
-// taps: acc + 0*x is a bit-exact no-op for finite x.  The planes are skewed by one word per
-// 4*D samples so that the lane stride (4*D + 1 words) is odd: conflict-free.
+// Output n, tap k reads x[n*D - k].  A thread owns R = 4 consecutive outputs n..n+3, and output n+i at tap k reads
+// exactly the sample output n read at tap k - i*D.  So only output n ("i = 0") loads from shared memory, one IQ
+// pair per tap, into a circular register delay line of L = 3*D entries per plane; outputs n+1..n+3 take theirs from
+// the line, D, 2D and 3D taps back.  The tap loop is unrolled over one trip round the line so that every line index
+// is static.  Each accumulator still sees its products in ascending tap order.  T is padded to a multiple of L with
+// zero taps: acc + 0*x is a bit-exact no-op for finite x.
+//
+// Round 2: the tile is staged as the RAW bytes it is (one aligned 32-bit global load and one 32-bit shared store per
+// two IQ pairs; round 1 converted to two float planes while staging, which took 31 % of the kernel's instructions at
+// 51 taps and four times the shared memory) and a pair is converted when the thread that owns it loads it: one
+// 16-bit LDS, then per byte a byte-permute into the float 65536 + b/128 and one subtraction (bit-identical to
+// (b - 128)/128, fmrx_device.cuh).  Per tap: 1 pair LDS + 4 conversion instructions + 1 broadcast tap LDS against
+// 8 FMUL + 8 FADD.  The tile is padded by one 32-bit word per 4*D pairs so that the lane stride (4*D pairs + 1 word)
+// is an odd number of words: conflict-free.
 
 constexpr int RFW_THREADS = 128;
 constexpr int RFW_R = 4;
 
 template <int D> struct RfWin {
     static constexpr int L = (RFW_R - 1) * D;       // delay-line length
-    static constexpr int SEG = RFW_R * D;           // samples per thread = skew period
-    static int tpad(int T) { return (T + L - 1) / L * L; }
-    static int wp(int T) { return (RF_COMPUTED - 1) * D + T + (tpad(T) - T); }     // staged samples per plane
-    static int plane(int T) { return wp(T) + wp(T) / SEG + 2; }
-    static size_t smem_bytes(int T) { return sizeof(float) * ((size_t)2 * plane(T) + 2 * RF_COMPUTED + tpad(T)); }
+    static constexpr int SEG = RFW_R * D;           // pairs per thread = padding period (even for every D in use)
+    static_assert(SEG % 2 == 0, "two pairs per staged word");
+    static __host__ __device__ int tpad(int T) { return (T + L - 1) / L * L; }
+    static __host__ __device__ int wp_max(int T) { return (RF_COMPUTED - 1) * D + T + (tpad(T) - T) + 1; }   // staged pairs (one more if the window starts on an odd pair)
+    static __host__ __device__ int words(int T) { return (wp_max(T) + 1) / 2 + (wp_max(T) + 1) / SEG + 2; }  // 32-bit words of the padded tile
+    static size_t smem_bytes(int T) { return sizeof(uint32_t) * (size_t)words(T) + sizeof(float) * ((size_t)2 * RF_COMPUTED + tpad(T)); }
 };
 
 template <int D> __global__ void __launch_bounds__(RFW_THREADS) k_rf_demod_win(const RfDemodArgs a)
 {
     using W = RfWin<D>;
     constexpr int L = W::L, SEG = W::SEG, R = RFW_R;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = a.T;
     const int Tpad = (T + L - 1) / L * L;
-    const int padl = Tpad - T;                  // staged samples in front of the window (zeros)
-    const int Wp = (RF_COMPUTED - 1) * D + T + padl;
-    const int plane = Wp + Wp / SEG + 2;
-    float *s_i = smem;
-    float *s_q = s_i + plane;
-    float *o_i = s_q + plane;                   // [RF_COMPUTED]
+    uint32_t *s_w = reinterpret_cast<uint32_t *>(smem_raw);                 // the raw tile, two pairs per word, padded
+    const unsigned short *s_p = reinterpret_cast<const unsigned short *>(s_w);
+    float *o_i = reinterpret_cast<float *>(s_w + W::words(T));              // [RF_COMPUTED]
     float *o_q = o_i + RF_COMPUTED;
-    float *s_c = o_q + RF_COMPUTED;             // [Tpad]
+    float *s_c = o_q + RF_COMPUTED;                                         // [Tpad]
 
     const int c = blockIdx.y;
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * RF_REAL;        // first demod sample of the tile
     const long long n_pairs = (long long)a.n_if * D;
-    // staged element l' (0..Wp) is chunk-local pair m = m_base + l' - padl
-    const long long m_base = (long long)(n0 - 1) * D - (T - 1);
     const uint8_t *iq = a.iq + (size_t)c * a.iq_stride;
     const uint8_t *hist = a.hist + (size_t)c * 2 * a.hist_pairs;
+    const uint16_t *iq16 = reinterpret_cast<const uint16_t *>(iq);
+    const uint16_t *hist16 = reinterpret_cast<const uint16_t *>(hist);
+    // staged pair l' (0..Wp) is chunk-local pair m_first + l'; the window starts `padl` pairs in front of the first
+    // sample a real tap reads (the padded taps read those; they only ever meet zero taps), one more if that makes its
+    // first pair 4-byte aligned in global memory
+    const long long m_base = (long long)(n0 - 1) * D - (T - 1);
+    const int padl0 = Tpad - T;
+    const int padl = padl0 + (int)((reinterpret_cast<uintptr_t>(iq16 + (m_base - padl0)) >> 1) & 1);
+    const long long m_first = m_base - padl;
+    const int Wp = (RF_COMPUTED - 1) * D + T + padl;
+    const int n_words = (Wp + 1) >> 1;
 
     for (int k = tid; k < Tpad; k += RFW_THREADS)
         s_c[k] = (k < T) ? a.taps[k] : 0.0f;
-    // Staging: one aligned 32-bit load brings two IQ pairs; the loads of a batch are all
-    // issued before the first conversion so that their latencies overlap.  The `padl`
-    // elements in front of the window only ever meet zero taps, so they may hold whatever
-    // finite data lies there; words that straddle the chunk (history in front, nothing
-    // behind) are assembled pair by pair.
-    const uint16_t *iq16 = reinterpret_cast<const uint16_t *>(iq);
-    const uint16_t *hist16 = reinterpret_cast<const uint16_t *>(hist);
-    const long long m_first = m_base - padl;                    // pair index of l' = 0
-    const int lead = (int)((reinterpret_cast<uintptr_t>(iq16 + m_first) >> 1) & 1);   // pairs in front to reach 4-byte alignment
-    const long long m_word0 = m_first - lead;
-    const int n_words = (Wp + lead + 1) >> 1;
     auto pair_at = [&](long long m) -> uint32_t {
         if (m >= 0)
             return m < n_pairs ? (uint32_t)iq16[m] : 0x8080u;      // (128,128) -> 0.0f, 0.0f
         const long long h = a.hist_pairs + m;
         return h >= 0 ? (uint32_t)hist16[h] : 0x8080u;
     };
-    constexpr int BATCH = 5;
+    // word j holds pairs l' = 2j, 2j+1 and sits at j + j / (SEG/2); the loads of a batch are all issued before the
+    // first store so that their latencies overlap; words that straddle the chunk (history in front, nothing behind)
+    // are assembled pair by pair
+    constexpr int BATCH = 6;
     for (int j0 = tid; j0 < n_words; j0 += BATCH * RFW_THREADS) {
         uint32_t v[BATCH];
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
             const int j = j0 + u * RFW_THREADS;
-            const long long m0 = m_word0 + 2 * (long long)j;
+            const long long m0 = m_first + 2 * (long long)j;
             v[u] = 0x80808080u;
             if (j < n_words) {
                 if (m0 >= 0 && m0 + 1 < n_pairs)
@@ -146,36 +149,27 @@ template <int D> __global__ void __launch_bounds__(RFW_THREADS) k_rf_demod_win(c
         }
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
-            const int lpa = 2 * (j0 + u * RFW_THREADS) - lead, lpb = lpa + 1;
-            if (lpa >= 0 && lpa < Wp) {
-                const int ad = lpa + lpa / SEG;
-                s_i[ad] = unpack_u8_byte<0>(v[u]);
-                s_q[ad] = unpack_u8_byte<1>(v[u]);
-            }
-            if (lpb < Wp) {
-                const int ad = lpb + lpb / SEG;
-                s_i[ad] = unpack_u8_byte<2>(v[u]);
-                s_q[ad] = unpack_u8_byte<3>(v[u]);
-            }
+            const int j = j0 + u * RFW_THREADS;
+            if (j < n_words)
+                s_w[j + j / (SEG / 2)] = v[u];
         }
     }
     __syncthreads();
 
-    // this thread: computed outputs o0..o0+3; sample of (i = 0, k = 0) sits at l' = b
+    // this thread: computed outputs o0..o0+3, o0 = 4 tid.  Output o0 at tap k reads staged pair tid*SEG + r0 - k,
+    // r0 = T - 1 + padl (the same for every thread); pair l' sits at 16-bit position l' + 2 (l' / SEG), i.e. for
+    // l' = tid*SEG + e at tid*(SEG + 2) + e + 2 (e / SEG)
     const int o0 = tid * R;
-    const int b = o0 * D + (T - 1) + padl;      // == tid*SEG + (T - 1 + padl)
-    const int r0 = T - 1 + padl;                // b - tid*SEG: the same for every thread
-    // skewed address of l' = b + e is  tid*(SEG+1) + (r0 + e) + floor((r0 + e)/SEG)
-    const int tbase = tid * (SEG + 1);
-    (void)b;
+    const int r0 = T - 1 + padl;
+    const unsigned short *tp = s_p + tid * (SEG + 2);
 
     float di[L], dq[L];                         // delay lines: slot (k mod L) holds the sample of tap k
 #pragma unroll
-    for (int m = 1; m <= L; m++) {              // "taps" -m: samples above b
+    for (int m = 1; m <= L; m++) {              // "taps" -m: the samples above tap 0's, for outputs o0+1..o0+3
         const int e = r0 + m;
-        const int ad = tbase + e + e / SEG;
-        di[L - m] = s_i[ad];
-        dq[L - m] = s_q[ad];
+        const uint32_t v = tp[e + 2 * (e / SEG)];
+        di[L - m] = unpack_u8_byte<0>(v);
+        dq[L - m] = unpack_u8_byte<1>(v);
     }
     float ai[R], aq[R];
 #pragma unroll
@@ -184,13 +178,16 @@ template <int D> __global__ void __launch_bounds__(RFW_THREADS) k_rf_demod_win(c
         aq[i] = 0.0f;
     }
     for (int k0 = 0; k0 < Tpad; k0 += L) {
+        // within a trip e = e_trip - j crosses at most one padding boundary: e / SEG = q - (j > rem)
+        const int e_trip = r0 - k0;             // >= 0 by construction of padl
+        const int q = e_trip / SEG, rem = e_trip - q * SEG;
+        const unsigned short *tq = tp + e_trip + 2 * q;
 #pragma unroll
         for (int j = 0; j < L; j++) {
-            const int e = r0 - (k0 + j);        // >= 0 by construction of padl
-            const int ad = tbase + e + e / SEG;
+            const uint32_t v = tq[-j - (j > rem ? 2 : 0)];
             const float ck = s_c[k0 + j];
             const float old_i = di[j], old_q = dq[j];          // tap k - L: output 3's sample
-            const float xi = s_i[ad], xq = s_q[ad];
+            const float xi = unpack_u8_byte<0>(v), xq = unpack_u8_byte<1>(v);
             di[j] = xi;
             dq[j] = xq;
             ai[0] = fadd(ai[0], fmul(ck, xi));
@@ -1701,16 +1698,17 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 const unsigned prog_a = smem_u32(&s_prog);
                 const unsigned ph_a = smem_u32(&s_ph[0]);
                 const unsigned h_a = smem_u32(&s_in[0]) + (unsigned)offsetof(PllIn, h1);
-                int prog = base;
+                const bool short_form = onehyp_short_ok(s_hdr_tad, s_hdr[1]);   // trigArg small, phaseEst's grid coarse: the six-operation step
+
+                int prog = base;             // warp 0's progress as last seen: a block old (the load is issued a block ahead, its latency off this warp's path)
                 for (int t = 0; t < cnt; t += 8) {
                     const int u0 = base + t;
                     int spin = 0;                // stay within PLL_LEAD1 of warp 0
 #ifdef FMRX_PLL_PROFILE
                     const long long pw0 = clock64();
 #endif
-                    do {
+                    while (prog != PLL_ABANDONED && u0 - prog > PLL_LEAD1 - 8 && ++spin < PLL_SPIN_LIMIT)
                         asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(prog) : "r"(prog_a) : "memory");
-                    } while (prog != PLL_ABANDONED && u0 - prog > PLL_LEAD1 - 8 && ++spin < PLL_SPIN_LIMIT);
 #ifdef FMRX_PLL_PROFILE
                     const long long pw1 = clock64();
                     if (lane == 0 && blockIdx.x == 0)
@@ -1718,8 +1716,12 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
 #endif
                     if (prog == PLL_ABANDONED || spin >= PLL_SPIN_LIMIT)
                         break;
+                    int prog_next;               // (consumed at the top of the next block)
+                    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(prog_next) : "r"(prog_a) : "memory");
                     const unsigned h_a0 = h_a + (unsigned)(u0 & (PLL_RING - 1)) * (unsigned)sizeof(PllIn);
                     const unsigned ph_a0 = ph_a + (unsigned)(u0 & (PLL_PH_RING - 1)) * 8u;
+                    // (loading the NEXT block's inputs here, under this block's steps, was tried: 5 % slower -- the 32 more
+                    // live registers cost the schedule more than the exposed LDS latency)
                     OneHypIn hs[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++)
@@ -1735,12 +1737,26 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     bool reduce = careful > 0;
                     if (!reduce) {
                         float amax = fabsf(ang);
+                        if (short_form) {
+                            float crs[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            ang = onehyp_predictor_step(k, hs[j], ang, integ, ph);
-                            phs[j] = ph;
-                            if (j < 7)
-                                amax = fmaxf(amax, fabsf(ang));
+                            for (int j = 0; j < 8; j++)
+                                crs[j] = p_faddf(hs[j].c, -hs[j].r);
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                ang = onehyp_predictor_step_short(k, hs[j].P, crs[j], ang, integ, ph);
+                                phs[j] = ph;
+                                if (j < 7)
+                                    amax = fmaxf(amax, fabsf(ang));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                ang = onehyp_predictor_step(k, hs[j], ang, integ, ph);
+                                phs[j] = ph;
+                                if (j < 7)
+                                    amax = fmaxf(amax, fabsf(ang));
+                            }
                         }
                         reduce = !(amax <= FMRX_ONEHYP_PI);
                         if (reduce)
@@ -1771,6 +1787,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                         s_prof1[2] += reduce;
                     }
 #endif
+                    prog = prog_next;
                 }
             }
         } else if (role == 1 && io_id < PLL_IO_WARPS) {
@@ -2180,6 +2197,46 @@ cudaError_t launch_pcm_pack(int16_t *pcm, const float *left, const float *right,
     if (n == 0)
         return cudaSuccess;
     k_pcm_pack<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pcm, left, right, n);
+    return cudaGetLastError();
+}
+
+// ---- the reference's RDS sketch (src/project.cpp:200-271): the two element-wise steps between the operators ----
+
+// :249-251 channel_squared[i] = channel_data[i] * channel_data[i]
+__global__ void k_square(float *out, const float *x, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = fmul(x[i], x[i]);
+}
+
+cudaError_t launch_square(float *out, const float *x, size_t n, cudaStream_t s)
+{
+    if (n == 0)
+        return cudaSuccess;
+    k_square<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, x, n);
+    return cudaGetLastError();
+}
+
+// :170 (the PLL's ncoOut from its trigArg), :259-263 (the channel delayed by `delay` samples, the first ones from the
+// carried state) and :269 / filter.cpp:182 (mixer): out[i] = 2 * (nco[i] * channel_shift[i])
+__global__ void k_rds_mix(float *out, const float *trig, const float *chan, const float *shift_state, int delay, size_t n,
+                          float scale, float adjust)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float nco = nco_from_trig(trig[i], scale, adjust);
+        const float c = i >= (size_t)delay ? chan[i - delay] : shift_state[i];
+        out[i] = mix2(nco, c);
+    }
+}
+
+cudaError_t launch_rds_mix(float *out, const float *trig, const float *chan, const float *shift_state, int delay, size_t n,
+                           float scale, float adjust, cudaStream_t s)
+{
+    if (n == 0)
+        return cudaSuccess;
+    k_rds_mix<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, trig, chan, shift_state, delay, n, scale, adjust);
     return cudaGetLastError();
 }
 

@@ -576,6 +576,20 @@ FMRX_HD float onehyp_predictor_step_reduced(const Consts &k, const OneHypIn &in,
     return p_fmaf(kq, 1.7484555e-07f, p_faddf(p_fmaf(-kq, 6.2831855f, -z), in.c));
 }
 
+// The short step, for groups in which trigArg is small and phaseEst's grid coarse (modes 2/3 once phaseEst has run
+// away: trigArg stays near 1.7 while phaseEst is in the thousands): the predictor does not round trigArg to its
+// float grid at all -- z = r + d instead of (B (+) (r (+) d)) (-) B, an error of at most ulp(trigArg)/2 = 2.4e-7 in
+// the angle, 6e-9 in Kp*errorD, against a phaseEst spacing of 1.2e-4 and more -- which takes three of the nine
+// dependent operations off its chain.  cr = c (-) r is formed off the chain.
+FMRX_HD float onehyp_predictor_step_short(const Consts &k, float P, float cr, float a, float &integ, float &ph)
+{
+    integ = p_faddf(integ, p_fmulf(k.ki, a));                        // :163
+    ph = p_faddf(ph, p_faddf(p_fmulf(k.kp, a), integ));              // :164
+    return p_faddf(cr, -p_faddf(ph, -P));
+}
+// ... usable while |trigArg| < 4 (its float spacing at most 2.4e-7) and |phaseEst| >= 1024 (its spacing at least 1.2e-4)
+FMRX_HD bool onehyp_short_ok(double tad, float ph) { return fabs(tad) < 4.0 && fabsf(ph) >= 1024.0f; }
+
 #define FMRX_ONEHYP_PI 3.14159274f       /* fl32(pi): the largest |angle| the unreduced step may carry */
 
 // trigArg as the reference forms it (:167): fl32(w*trigOffset + (double)phaseEst), held in a double

@@ -562,12 +562,17 @@ extern "C" int pll_model_onehyp_float(const float *pilot, int n, float freq, flo
             }
             // predictor
             float pi_ = c.integ, pp = c.ph;
+            const bool short_form = onehyp_short_ok(c.tad, c.ph);  // (decided per group, in the header)
+            stats[3 + 0] += 0;
+            if (short_form && g < (1 << 17))
+                pll_model_grp_fail[g] |= 2;                        // (bit 1: the group ran the short predictor step)
             float a = onehyp_first_angle(pilot[base], c.tad);      // the angle from the exact trigArg before the group
             for (int j0 = 0; j0 < cnt; j0 += 8) {          // as the predictor warp: blocks of 8, again with the reduction if an angle left [-pi, pi]
                 const float a0 = a, i0 = pi_, p0 = pp;
                 float amax = fabsf(a);
                 for (int j = j0; j < j0 + 8 && j < cnt; j++) {
-                    a = onehyp_predictor_step(k, in1[j], a, pi_, pp);
+                    a = short_form ? onehyp_predictor_step_short(k, in1[j].P, in1[j].c + -in1[j].r, a, pi_, pp)
+                                   : onehyp_predictor_step(k, in1[j], a, pi_, pp);
                     pph[j] = pp;
                     if (j + 1 < j0 + 8)
                         amax = fmaxf(amax, fabsf(a));
