@@ -256,6 +256,18 @@ int fmrx_rds_process(fmrx_rds *h, const float *demod, size_t n, float *mixer_out
                      float *channel_out, float *carrier_out);
 int fmrx_rds_pll_state(fmrx_rds *h, float out[6]);
 
+/* ---------------------------------------------------------------------- */
+/* Spectrum tap: estimatePSD, src/fourier.cpp:35-117 (with its DFT, :14-22).  */
+/* HOST pointers; freq and psd receive freq_bins/2 floats (Hz, dB); samples    */
+/* beyond whole segments of freq_bins are ignored, as in the reference.        */
+/* A diagnostic (validation plots of any fmrx_read_stage output): computed in  */
+/* double behind the reference's float window, so it agrees with the           */
+/* reference to the reference's own float accuracy, not bit for bit.           */
+/* freq_bins <= 2048.                                                          */
+/* ---------------------------------------------------------------------- */
+int fmrx_estimate_psd(float *freq, float *psd, const float *samples, size_t n,
+                      int freq_bins, float Fs);
+
 #ifdef __cplusplus
 }
 #endif

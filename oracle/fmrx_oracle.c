@@ -520,3 +520,51 @@ void orc_rds_block(orc_rds *r, const float *demod, int n, float *mixer_out, floa
         memcpy(carrier_nco, car, sizeof(float) * n);
     free(chan); free(sq); free(car); free(shift);
 }
+
+
+/* ---- spectrum estimate, src/fourier.cpp:35-117 (estimatePSD with its DFT, :14-22) ----------
+ * Restated operation for operation: float Hann window from a double sin^2 (:55), float
+ * windowed samples (:79), the DFT as a running complex<float> sum of x[k]*exp(-2 pi i k m/N)
+ * with the exponent formed in double and rounded to float before std::exp (:18-19), power
+ * (4/(Fs*N))*|X^2| (:94), 10 log10 (:97), mean over the segments (:104-111).  The complex
+ * float exp of libstdc++ is cexpf: expf(0) * (cosf, sinf). */
+int orc_estimate_psd(float *freq, float *psd, const float *samples, int n, int freq_bins, float Fs)
+{
+    const float df = Fs / freq_bins;                                   /* :43 */
+    const int half = freq_bins / 2;
+    const int num_segments = n / freq_bins;                            /* :63 */
+    float *hann = (float *)malloc(sizeof(float) * freq_bins);
+    float *win = (float *)malloc(sizeof(float) * freq_bins);
+    double *acc = (double *)calloc(half, sizeof(double));
+    for (int i = 0; i < half; i++)
+        freq[i] = i * df;                                              /* :50 */
+    for (int i = 0; i < freq_bins; i++) {
+        const double s = sin(i * 3.14159265358979323846 / freq_bins);
+        hann[i] = (float)(s * s);                                      /* :55 std::pow(double, 2) */
+    }
+    for (int i = 0; i < half; i++)
+        psd[i] = 0.0f;
+    for (int k = 0; k < num_segments; k++) {
+        for (int i = 0; i < freq_bins; i++)
+            win[i] = samples[k * freq_bins + i] * hann[i];            /* :79 */
+        for (int m = 0; m < half; m++) {
+            float re = 0.0f, im = 0.0f;                                /* :15 */
+            for (int j = 0; j < freq_bins; j++) {
+                const float ang = (float)(-2 * 3.14159265358979323846 * (j * m) / freq_bins);   /* :18: double expression, float imaginary part */
+                const float cr = cosf(ang), ci = sinf(ang);           /* std::exp(complex<float>(0, ang)) */
+                re = re + win[j] * cr;                                 /* :19 float * complex<float>, complex += */
+                im = im + win[j] * ci;
+            }
+            /* :94 std::pow(complex<float>, 2) = z*z, std::abs -> hypotf */
+            const float zr = re * re - im * im, zi = re * im + re * im;
+            float v = (4 / (Fs * freq_bins)) * hypotf(zr, zi);
+            v = 10 * log10f(v);                                        /* :97 (float overload) */
+            acc[m] += 0.0;                                             /* (kept for symmetry with the list-then-sum of :100-111) */
+            psd[m] = psd[m] + v;                                       /* :106 float accumulation, segment order */
+        }
+    }
+    for (int m = 0; m < half; m++)
+        psd[m] = psd[m] / num_segments;                                /* :110 */
+    free(hann); free(win); free(acc);
+    return half;
+}

@@ -63,6 +63,9 @@ orc_rds *orc_rds_create(float bp_fs, int taps, int channel_delay);
 void orc_rds_destroy(orc_rds *r);
 void orc_rds_block(orc_rds *r, const float *demod, int n, float *mixer_out, float *channel, float *carrier_nco);
 
+/* ---- spectrum estimate (src/fourier.cpp:35-117): freq, psd receive freq_bins/2 floats; returns that count ---- */
+int orc_estimate_psd(float *freq, float *psd, const float *samples, int n, int freq_bins, float Fs);
+
 /* ---- mode table (src/project.cpp:304-364) ------------------------------ */
 typedef struct {
     int mode;

@@ -124,6 +124,17 @@ class _OpsMixin:
         f(_fp(out), C.byref(pi), C.byref(pq), _fp(i_ds), _fp(q_ds), len(i_ds))
         return out, float(pi.value), float(pq.value)
 
+    def estimate_psd(self, samples, freq_bins, Fs):
+        """estimatePSD (src/fourier.cpp:35-117) -> (freq, psd)"""
+        x = np.ascontiguousarray(samples, np.float32)
+        f = np.zeros(freq_bins // 2, np.float32)
+        p = np.zeros(freq_bins // 2, np.float32)
+        fn = self._fn("estimate_psd")
+        fn.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_float]
+        fn.restype = C.c_int
+        fn(_fp(f), _fp(p), _fp(x), len(x), freq_bins, Fs)
+        return f, p
+
     def mixer(self, a, b):
         a = np.ascontiguousarray(a, np.float32)
         b = np.ascontiguousarray(b, np.float32)

@@ -19,7 +19,8 @@
 #include <cstring>
 #include <vector>
 
-#include "filter.h"   /* reference include/filter.h via -I */
+#include "filter.h"
+#include "fourier.h"   /* reference include/filter.h via -I */
 #include "iofunc.h"   /* reference include/iofunc.h via -I */
 
 typedef std::vector<float> vf;
@@ -237,6 +238,17 @@ void ref_rds_block(ref_rds *r, const float *demod, int n, float *mixer_out, floa
     out_copy(mixer_out, mixer_data);
     if (channel) out_copy(channel, channel_data);
     if (carrier_nco) out_copy(carrier_nco, carrier_data);
+}
+
+
+/* ---- the reference's spectrum estimate (src/fourier.cpp:35-117), its own code ---- */
+int ref_estimate_psd(float *freq, float *psd, const float *samples, int n, int freq_bins, float Fs)
+{
+    vf f, p, x(samples, samples + n);
+    estimatePSD(f, p, x, freq_bins, Fs);
+    out_copy(freq, f);
+    out_copy(psd, p);
+    return (int)p.size();
 }
 
 } /* extern "C" */

@@ -42,6 +42,7 @@ ABI_SYMBOLS = (
     "fmrx_long_create", "fmrx_long_destroy", "fmrx_long_shard", "fmrx_long_process", "fmrx_long_process_device",
     "fmrx_long_last_ms", "fmrx_long_pll_state",
     "fmrx_rds_create", "fmrx_rds_destroy", "fmrx_rds_reset", "fmrx_rds_process", "fmrx_rds_pll_state",
+    "fmrx_estimate_psd",
 )
 
 
@@ -125,6 +126,7 @@ def load() -> C.CDLL:
     L.fmrx_rds_reset.argtypes = [C.c_void_p]
     L.fmrx_rds_process.argtypes = [C.c_void_p, _f32p, C.c_size_t, _f32p, _f32p, _f32p]
     L.fmrx_rds_pll_state.argtypes = [C.c_void_p, _f32p]
+    L.fmrx_estimate_psd.argtypes = [_f32p, _f32p, _f32p, C.c_size_t, C.c_int, C.c_float]
     L.fmrx_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.fmrx_last_timing.argtypes = [C.c_void_p, _f32p]
     _lib = L
@@ -430,3 +432,13 @@ class RdsFront:
         st = np.zeros(6, np.float32)
         _check(self._L.fmrx_rds_pll_state(self._h, _fp(st)), "fmrx_rds_pll_state")
         return st
+
+
+def estimatePSD(samples, freq_bins: int, Fs: float):
+    """estimatePSD, src/fourier.cpp:35-117: returns (freq [Hz], psd [dB]), ``freq_bins // 2`` floats each."""
+    L = load()
+    x = np.ascontiguousarray(samples, np.float32)
+    f = np.zeros(freq_bins // 2, np.float32)
+    p = np.zeros(freq_bins // 2, np.float32)
+    _check(L.fmrx_estimate_psd(_fp(f), _fp(p), _fp(x), len(x), freq_bins, Fs), "fmrx_estimate_psd")
+    return f, p

@@ -1510,3 +1510,26 @@ extern "C" int fmrx_rds_pll_state(fmrx_rds *r, float out[6])
     std::memcpy(out, st, 6 * sizeof(float));
     return FMRX_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Spectrum tap: estimatePSD, src/fourier.cpp:35-117
+// ---------------------------------------------------------------------------
+extern "C" int fmrx_estimate_psd(float *freq, float *psd, const float *samples, size_t n, int freq_bins, float Fs)
+{
+    // (freq_bins <= 2048: the twiddle table and the window live in the default 48 KB of shared memory)
+    if (!freq || !psd || !samples || freq_bins < 2 || freq_bins > 2048 || !(Fs > 0) || n / freq_bins < 1 || n / freq_bins > 0x7fffffffu)
+        return FMRX_ERR_ARG;
+    const int half = freq_bins / 2;
+    const int n_seg = static_cast<int>(n / freq_bins);                   // :63 (samples beyond whole segments are ignored)
+    const float df = Fs / freq_bins;                                     // :43
+    for (int i = 0; i < half; i++)
+        freq[i] = i * df;                                                // :50
+    DevBuf d_x, d_p;
+    const size_t used = static_cast<size_t>(n_seg) * freq_bins;
+    CU(d_x.alloc(used * sizeof(float)));
+    CU(d_p.alloc(half * sizeof(float)));
+    CU(cudaMemcpy(d_x.p, samples, used * sizeof(float), cudaMemcpyHostToDevice));
+    CU(launch_psd(d_p.as<float>(), d_x.as<float>(), n_seg, freq_bins, Fs, 0));
+    CU(cudaMemcpy(psd, d_p.p, half * sizeof(float), cudaMemcpyDeviceToHost));
+    return FMRX_OK;
+}

@@ -103,4 +103,7 @@ cudaError_t launch_square(float *out, const float *x, size_t n, cudaStream_t s);
 cudaError_t launch_rds_mix(float *out, const float *trig, const float *chan, const float *shift_state, int delay, size_t n,
                            float scale, float adjust, cudaStream_t s);
 
+// spectrum tap: the reference's estimatePSD (src/fourier.cpp:35-117); freq_bins * 20 bytes of dynamic shared memory
+cudaError_t launch_psd(float *psd, const float *samples, int n_seg, int freq_bins, float Fs, cudaStream_t s);
+
 }  // namespace fmrx

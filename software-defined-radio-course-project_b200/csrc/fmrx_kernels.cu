@@ -2240,4 +2240,61 @@ cudaError_t launch_rds_mix(float *out, const float *trig, const float *chan, con
     return cudaGetLastError();
 }
 
+// ---- spectrum tap: the reference's estimatePSD (src/fourier.cpp:35-117) ---------------------------------------
+// Hann-windowed segments of freq_bins samples, the DFT of each (:14-22), power (4/(Fs N)) |X|^2 in dB, mean over the
+// segments.  The reference accumulates its DFT in complex<float> with libm's cosf/sinf; here the window and the
+// windowed samples are the reference's floats and everything behind them is double (twiddles from a shared table,
+// index (j m) mod N kept incrementally), so the result is the same estimate to the reference's own float accuracy --
+// a diagnostic, compared with a tolerance, not a parity-critical path.  One CTA per frequency bin; its threads take
+// the segments round robin.
+__global__ void __launch_bounds__(128) k_psd(float *psd, const float *samples, int n_seg, int N, float Fs)
+{
+    extern __shared__ __align__(16) double2 s_tw[];      // [N] e^{-2 pi i r / N}
+    float *s_hann = reinterpret_cast<float *>(s_tw + N); // [N]
+    __shared__ double s_red[128];
+    const int m = blockIdx.x, tid = threadIdx.x;
+    for (int r = tid; r < N; r += blockDim.x) {
+        double sn, cs;
+        sincospi(-2.0 * (double)r / (double)N, &sn, &cs);
+        s_tw[r] = make_double2(cs, sn);
+        const double h = sin((double)r * 3.14159265358979323846 / (double)N);       // :55
+        s_hann[r] = (float)(h * h);
+    }
+    __syncthreads();
+    double acc = 0.0;
+    for (int sgm = tid; sgm < n_seg; sgm += blockDim.x) {
+        const float *x = samples + (size_t)sgm * N;
+        double re = 0.0, im = 0.0;
+        int r = 0;
+        for (int j = 0; j < N; j++) {
+            const double w = (double)fmul(x[j], s_hann[j]);                          // :79 (float product)
+            const double2 t = s_tw[r];
+            re = __fma_rn(w, t.x, re);
+            im = __fma_rn(w, t.y, im);
+            r += m;
+            r -= r >= N ? N : 0;
+        }
+        const double p = (4.0 / ((double)Fs * (double)N)) * (re * re + im * im);    // :94
+        acc += 10.0 * log10(p);                                                      // :97
+    }
+    s_red[tid] = acc;
+    __syncthreads();
+    for (int st = 64; st > 0; st >>= 1) {
+        if (tid < st)
+            s_red[tid] += s_red[tid + st];
+        __syncthreads();
+    }
+    if (tid == 0)
+        psd[m] = (float)(s_red[0] / (double)n_seg);                                  // :110
+}
+
+cudaError_t launch_psd(float *psd, const float *samples, int n_seg, int freq_bins, float Fs, cudaStream_t s)
+{
+    if (freq_bins < 2 || n_seg < 1)
+        return cudaSuccess;
+    const size_t smem = (size_t)freq_bins * (sizeof(double2) + sizeof(float));
+    k_psd<<<freq_bins / 2, 128, smem, s>>>(psd, samples, n_seg, freq_bins, Fs);
+    return cudaGetLastError();
+}
+
 }  // namespace fmrx
