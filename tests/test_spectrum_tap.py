@@ -2,7 +2,9 @@
 reference its own unit tests touch (test/*_unittest.cpp cover the Fourier utilities).
 CPU: the oracle's operation-for-operation restatement is BIT-identical to the reference's compiled fourier.cpp.
 GPU: fmrx_estimate_psd (double precision behind the reference's float window) agrees with it to the reference's own
-float accuracy: within 0.01 dB on every bin within 70 dB of the strongest."""
+float accuracy.  That accuracy is set by the reference's DFT: it rounds the angle -2 pi k m / N to a float BEFORE
+cosf/sinf (:18), an absolute error of up to 2e-4 rad once k m reaches 10^6 (1024+ bins), which shows in the weak
+upper bins -- so: within 0.01 dB on the bins within 30 dB of the strongest, 0.25 dB within 70 dB."""
 import numpy as np
 import pytest
 
@@ -33,8 +35,9 @@ def test_cuda_psd_matches_oracle_within_float_accuracy(fm, port, bins, segments)
     fo, po = port.estimate_psd(x, bins, 240e3)
     fg, pg = fm.estimatePSD(x, bins, 240e3)
     assert_bits_equal(fg, fo, "freq")
-    strong = po > po.max() - 70.0
-    assert np.abs(pg - po)[strong].max() < 0.01, np.abs(pg - po)[strong].max()
+    for span, tol in ((30.0, 0.01), (70.0, 0.25)):
+        sel = po > po.max() - span
+        assert np.abs(pg - po)[sel].max() < tol, (span, np.abs(pg - po)[sel].max())
     assert np.argmax(pg) == np.argmax(po)
     with pytest.raises(fm.FmrxError):
         fm.estimatePSD(x, 4096, 240e3)
