@@ -43,9 +43,9 @@ METRIC = "input IQ Msamples/s (mode 0 stereo)"
 UNIT = "Msamples/s"
 MODE, TAPS = 0, 51
 RF_FS = 2.4e6
-# warp-instructions the chain warp of k_pll issues per step in its steady-state loop (counted in the SASS of
-# pll_table_group: profiles/r02_k_pll_chain_sass.txt)
-PLL_CHAIN_INSTR_PER_STEP = 20
+# warp-instructions the chain warp of k_pll issues per step in its steady-state loop: 403 SASS instructions per
+# block of 16 steps in the ncu source view of pll_table_group (profiles/r02_ncu_summary.md)
+PLL_CHAIN_INSTR_PER_STEP = 25.2
 
 
 def parse_args():
@@ -574,10 +574,12 @@ def main_b200(args):
                 "share_of_step": pll_ms_step / ms_step,
                 "limiter": "issue",
                 "issue": {"what": "k_pll is one dependent recurrence per capture, run by ONE warp per capture: its bound is that warp's "
-                                  "instruction issue (1 instruction per 2 cycles on this machine), not HBM",
+                                  "instruction issue and the latency of its dependent chain, not HBM",
                           "chain_warp_instructions_per_step": PLL_CHAIN_INSTR_PER_STEP, "cycles_per_step": cyc_step,
-                          "achieved_ipc": PLL_CHAIN_INSTR_PER_STEP / cyc_step, "peak_ipc": 0.5,
-                          "frac": PLL_CHAIN_INSTR_PER_STEP / cyc_step / 0.5, "sm_mhz": sm_mhz},
+                          "achieved_ipc": PLL_CHAIN_INSTR_PER_STEP / cyc_step, "peak_ipc": 1.0,
+                          "frac": PLL_CHAIN_INSTR_PER_STEP / cyc_step, "sm_mhz": sm_mhz,
+                          "note": "peak = one instruction per cycle from one warp; inside the loop the warp issues in 57 % of its cycles "
+                                  "(44.4 cycles per step), the rest are dependency waits of the recurrence itself"},
                 "note": "hbm fraction is tiny by construction; see `issue` and pll_ns_per_sample"}
     total_k = sum(kern.values())
     # FP32 issue-rate view of the FIR kernels: one MAC = FMUL + FADD (bit-exact, unfused)

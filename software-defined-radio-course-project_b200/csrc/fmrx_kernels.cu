@@ -87,39 +87,38 @@ template <int D> struct RfWin {
     static __host__ __device__ int tpad(int T) { return (T + L - 1) / L * L; }
     static __host__ __device__ int wp_max(int T) { return (RF_COMPUTED - 1) * D + T + (tpad(T) - T) + 1; }   // staged pairs (one more if the window starts on an odd pair)
     static __host__ __device__ int words(int T) { return (wp_max(T) + 1) / 2 + (wp_max(T) + 1) / SEG + 2; }  // 32-bit words of the padded tile
-    static size_t smem_bytes(int T) { return sizeof(uint32_t) * (size_t)words(T) + sizeof(float) * ((size_t)2 * RF_COMPUTED + tpad(T)); }
+    static size_t smem_bytes(int T) { return sizeof(uint32_t) * (size_t)2 * words(T) + sizeof(float) * ((size_t)2 * RF_COMPUTED + tpad(T)); }   // two tiles
 };
 
-template <int D> __global__ void __launch_bounds__(RFW_THREADS) k_rf_demod_win(const RfDemodArgs a)
+// A CTA takes RFW_TILES_MAX (fewer on short chunks) consecutive tiles of one capture and keeps two raw tiles in shared
+// memory: the bytes of tile i+1 arrive by cp.async (4 bytes per request: the tile starts on an arbitrary IQ pair, and
+// the padded layout breaks 16-byte runs anyway) while tile i is computed.  Before this the kernel spent two thirds of
+// its time at 51 taps waiting for the tile it was about to compute (ncu source view, profiles/r02_ncu_summary.md).
+constexpr int RFW_TILES_MAX = 8;
+
+template <int D> __global__ void __launch_bounds__(RFW_THREADS) k_rf_demod_win(const RfDemodArgs a, const int tiles_per_cta)
 {
     using W = RfWin<D>;
     constexpr int L = W::L, SEG = W::SEG, R = RFW_R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = a.T;
     const int Tpad = (T + L - 1) / L * L;
-    uint32_t *s_w = reinterpret_cast<uint32_t *>(smem_raw);                 // the raw tile, two pairs per word, padded
-    const unsigned short *s_p = reinterpret_cast<const unsigned short *>(s_w);
-    float *o_i = reinterpret_cast<float *>(s_w + W::words(T));              // [RF_COMPUTED]
+    const int words = W::words(T);
+    uint32_t *s_buf = reinterpret_cast<uint32_t *>(smem_raw);               // two raw tiles, two pairs per word, padded
+    float *o_i = reinterpret_cast<float *>(s_buf + 2 * words);              // [RF_COMPUTED]
     float *o_q = o_i + RF_COMPUTED;
     float *s_c = o_q + RF_COMPUTED;                                         // [Tpad]
 
     const int c = blockIdx.y;
     const int tid = threadIdx.x;
-    const int n0 = blockIdx.x * RF_REAL;        // first demod sample of the tile
     const long long n_pairs = (long long)a.n_if * D;
     const uint8_t *iq = a.iq + (size_t)c * a.iq_stride;
     const uint8_t *hist = a.hist + (size_t)c * 2 * a.hist_pairs;
     const uint16_t *iq16 = reinterpret_cast<const uint16_t *>(iq);
     const uint16_t *hist16 = reinterpret_cast<const uint16_t *>(hist);
-    // staged pair l' (0..Wp) is chunk-local pair m_first + l'; the window starts `padl` pairs in front of the first
-    // sample a real tap reads (the padded taps read those; they only ever meet zero taps), one more if that makes its
-    // first pair 4-byte aligned in global memory
-    const long long m_base = (long long)(n0 - 1) * D - (T - 1);
     const int padl0 = Tpad - T;
-    const int padl = padl0 + (int)((reinterpret_cast<uintptr_t>(iq16 + (m_base - padl0)) >> 1) & 1);
-    const long long m_first = m_base - padl;
-    const int Wp = (RF_COMPUTED - 1) * D + T + padl;
-    const int n_words = (Wp + 1) >> 1;
+    const int n_tiles = (a.n_if + RF_REAL - 1) / RF_REAL;
+    const int tile_lo = blockIdx.x * tiles_per_cta, tile_hi = min(n_tiles, tile_lo + tiles_per_cta);
 
     for (int k = tid; k < Tpad; k += RFW_THREADS)
         s_c[k] = (k < T) ? a.taps[k] : 0.0f;
@@ -129,97 +128,111 @@ template <int D> __global__ void __launch_bounds__(RFW_THREADS) k_rf_demod_win(c
         const long long h = a.hist_pairs + m;
         return h >= 0 ? (uint32_t)hist16[h] : 0x8080u;
     };
-    // word j holds pairs l' = 2j, 2j+1 and sits at j + j / (SEG/2); the loads of a batch are all issued before the
-    // first store so that their latencies overlap; words that straddle the chunk (history in front, nothing behind)
-    // are assembled pair by pair
-    constexpr int BATCH = 6;
-    for (int j0 = tid; j0 < n_words; j0 += BATCH * RFW_THREADS) {
-        uint32_t v[BATCH];
-#pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            const int j = j0 + u * RFW_THREADS;
+    // Staged pair l' (0..Wp) of a tile is chunk-local pair m_first + l'; the window starts `padl` pairs in front of the
+    // first sample a real tap reads (the padded taps read those; they only ever meet zero taps), one more if that makes
+    // its first pair 4-byte aligned in global memory.  Word j holds pairs l' = 2j, 2j+1 and sits at j + j / (SEG/2).
+    auto tile_padl = [&](int tile) {
+        const long long m_base = (long long)(tile * RF_REAL - 1) * D - (T - 1);
+        return padl0 + (int)((reinterpret_cast<uintptr_t>(iq16 + (m_base - padl0)) >> 1) & 1);
+    };
+    auto stage = [&](int tile, uint32_t *s_w) {
+        const int padl = tile_padl(tile);
+        const long long m_first = (long long)(tile * RF_REAL - 1) * D - (T - 1) - padl;
+        const int Wp = (RF_COMPUTED - 1) * D + T + padl;
+        const int n_words = (Wp + 1) >> 1;
+        for (int j = tid; j < n_words; j += RFW_THREADS) {
             const long long m0 = m_first + 2 * (long long)j;
-            v[u] = 0x80808080u;
-            if (j < n_words) {
-                if (m0 >= 0 && m0 + 1 < n_pairs)
-                    v[u] = *reinterpret_cast<const uint32_t *>(iq16 + m0);
-                else
-                    v[u] = pair_at(m0) | (pair_at(m0 + 1) << 16);
+            uint32_t *dst = s_w + j + j / (SEG / 2);
+            if (m0 >= 0 && m0 + 1 < n_pairs) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(iq16 + m0) : "memory");
+            } else {             // words that straddle the chunk (history in front, nothing behind): assembled pair by pair
+                *dst = pair_at(m0) | (pair_at(m0 + 1) << 16);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    if (tile_lo < tile_hi)
+        stage(tile_lo, s_buf);
+    for (int tile = tile_lo; tile < tile_hi; tile++) {
+        uint32_t *s_w = s_buf + ((tile - tile_lo) & 1) * words;
+        if (tile + 1 < tile_hi) {
+            stage(tile + 1, s_buf + ((tile + 1 - tile_lo) & 1) * words);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+
+        const unsigned short *s_p = reinterpret_cast<const unsigned short *>(s_w);
+        const int n0 = tile * RF_REAL;              // first demod sample of the tile
+        const int padl = tile_padl(tile);
+        // this thread: computed outputs o0..o0+3, o0 = 4 tid.  Output o0 at tap k reads staged pair tid*SEG + r0 - k,
+        // r0 = T - 1 + padl (the same for every thread); pair l' sits at 16-bit position l' + 2 (l' / SEG), i.e. for
+        // l' = tid*SEG + e at tid*(SEG + 2) + e + 2 (e / SEG)
+        const int o0 = tid * R;
+        const int r0 = T - 1 + padl;
+        const unsigned short *tp = s_p + tid * (SEG + 2);
+
+        float di[L], dq[L];                         // delay lines: slot (k mod L) holds the sample of tap k
+#pragma unroll
+        for (int m = 1; m <= L; m++) {              // "taps" -m: the samples above tap 0's, for outputs o0+1..o0+3
+            const int e = r0 + m;
+            const uint32_t v = tp[e + 2 * (e / SEG)];
+            di[L - m] = unpack_u8_byte<0>(v);
+            dq[L - m] = unpack_u8_byte<1>(v);
+        }
+        float ai[R], aq[R];
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            ai[i] = 0.0f;
+            aq[i] = 0.0f;
+        }
+        for (int k0 = 0; k0 < Tpad; k0 += L) {
+            // within a trip e = e_trip - j crosses at most one padding boundary: e / SEG = q - (j > rem)
+            const int e_trip = r0 - k0;             // >= 0 by construction of padl
+            const int q = e_trip / SEG, rem = e_trip - q * SEG;
+            const unsigned short *tq = tp + e_trip + 2 * q;
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                const uint32_t v = tq[-j - (j > rem ? 2 : 0)];
+                const float ck = s_c[k0 + j];
+                const float old_i = di[j], old_q = dq[j];          // tap k - L: output 3's sample
+                const float xi = unpack_u8_byte<0>(v), xq = unpack_u8_byte<1>(v);
+                di[j] = xi;
+                dq[j] = xq;
+                ai[0] = fadd(ai[0], fmul(ck, xi));
+                aq[0] = fadd(aq[0], fmul(ck, xq));
+                ai[1] = fadd(ai[1], fmul(ck, di[(j + L - D) % L]));
+                aq[1] = fadd(aq[1], fmul(ck, dq[(j + L - D) % L]));
+                ai[2] = fadd(ai[2], fmul(ck, di[(j + L - 2 * D) % L]));
+                aq[2] = fadd(aq[2], fmul(ck, dq[(j + L - 2 * D) % L]));
+                ai[3] = fadd(ai[3], fmul(ck, old_i));
+                aq[3] = fadd(aq[3], fmul(ck, old_q));
             }
         }
 #pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            const int j = j0 + u * RFW_THREADS;
-            if (j < n_words)
-                s_w[j + j / (SEG / 2)] = v[u];
+        for (int i = 0; i < R; i++) {
+            o_i[o0 + i] = ai[i];
+            o_q[o0 + i] = aq[i];
         }
-    }
-    __syncthreads();
+        __syncthreads();         // (also: every thread is done with this tile's bytes -- the next iteration stages over them)
 
-    // this thread: computed outputs o0..o0+3, o0 = 4 tid.  Output o0 at tap k reads staged pair tid*SEG + r0 - k,
-    // r0 = T - 1 + padl (the same for every thread); pair l' sits at 16-bit position l' + 2 (l' / SEG), i.e. for
-    // l' = tid*SEG + e at tid*(SEG + 2) + e + 2 (e / SEG)
-    const int o0 = tid * R;
-    const int r0 = T - 1 + padl;
-    const unsigned short *tp = s_p + tid * (SEG + 2);
-
-    float di[L], dq[L];                         // delay lines: slot (k mod L) holds the sample of tap k
+        float *demod = a.demod + (size_t)c * a.if_stride + a.if_off;
 #pragma unroll
-    for (int m = 1; m <= L; m++) {              // "taps" -m: the samples above tap 0's, for outputs o0+1..o0+3
-        const int e = r0 + m;
-        const uint32_t v = tp[e + 2 * (e / SEG)];
-        di[L - m] = unpack_u8_byte<0>(v);
-        dq[L - m] = unpack_u8_byte<1>(v);
-    }
-    float ai[R], aq[R];
-#pragma unroll
-    for (int i = 0; i < R; i++) {
-        ai[i] = 0.0f;
-        aq[i] = 0.0f;
-    }
-    for (int k0 = 0; k0 < Tpad; k0 += L) {
-        // within a trip e = e_trip - j crosses at most one padding boundary: e / SEG = q - (j > rem)
-        const int e_trip = r0 - k0;             // >= 0 by construction of padl
-        const int q = e_trip / SEG, rem = e_trip - q * SEG;
-        const unsigned short *tq = tp + e_trip + 2 * q;
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            const uint32_t v = tq[-j - (j > rem ? 2 : 0)];
-            const float ck = s_c[k0 + j];
-            const float old_i = di[j], old_q = dq[j];          // tap k - L: output 3's sample
-            const float xi = unpack_u8_byte<0>(v), xq = unpack_u8_byte<1>(v);
-            di[j] = xi;
-            dq[j] = xq;
-            ai[0] = fadd(ai[0], fmul(ck, xi));
-            aq[0] = fadd(aq[0], fmul(ck, xq));
-            ai[1] = fadd(ai[1], fmul(ck, di[(j + L - D) % L]));
-            aq[1] = fadd(aq[1], fmul(ck, dq[(j + L - D) % L]));
-            ai[2] = fadd(ai[2], fmul(ck, di[(j + L - 2 * D) % L]));
-            aq[2] = fadd(aq[2], fmul(ck, dq[(j + L - 2 * D) % L]));
-            ai[3] = fadd(ai[3], fmul(ck, old_i));
-            aq[3] = fadd(aq[3], fmul(ck, old_q));
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < R; i++) {
-        o_i[o0 + i] = ai[i];
-        o_q[o0 + i] = aq[i];
-    }
-    __syncthreads();
-
-    float *demod = a.demod + (size_t)c * a.if_stride + a.if_off;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const int o = tid + r * RFW_THREADS;    // coalesced
-        const int n = n0 - 1 + o;
-        if (o >= 1 && n < a.n_if) {
-            demod[n] = fm_discriminate(o_i[o], o_q[o], o_i[o - 1], o_q[o - 1]);
-            if (a.i_ds) {
-                const size_t g = (size_t)c * a.stage_stride + a.stage_off + n;
-                a.i_ds[g] = o_i[o];
-                a.q_ds[g] = o_q[o];
+        for (int r = 0; r < R; r++) {
+            const int o = tid + r * RFW_THREADS;    // coalesced
+            const int n = n0 - 1 + o;
+            if (o >= 1 && n < a.n_if) {
+                demod[n] = fm_discriminate(o_i[o], o_q[o], o_i[o - 1], o_q[o - 1]);
+                if (a.i_ds) {
+                    const size_t g = (size_t)c * a.stage_stride + a.stage_off + n;
+                    a.i_ds[g] = o_i[o];
+                    a.q_ds[g] = o_q[o];
+                }
             }
         }
+        __syncthreads();         // o_i / o_q are free again
     }
 }
 
@@ -240,8 +253,13 @@ template <int D> static cudaError_t launch_rf_demod_win(const RfDemodArgs &a, in
         }
     }
     const int tiles = (a.n_if + RF_REAL - 1) / RF_REAL;
-    dim3 grid(tiles, n_captures);
-    k_rf_demod_win<D><<<grid, RFW_THREADS, smem, s>>>(a);
+    // consecutive tiles per CTA (the next tile's bytes arrive while one is computed), fewer on short chunks so that
+    // the grid still fills the machine
+    int per = RFW_TILES_MAX;
+    while (per > 1 && (long long)((tiles + per - 1) / per) * n_captures < 4 * 148)
+        per >>= 1;
+    dim3 grid((tiles + per - 1) / per, n_captures);
+    k_rf_demod_win<D><<<grid, RFW_THREADS, smem, s>>>(a, per);
     return cudaGetLastError();
 }
 
