@@ -431,9 +431,11 @@ def main_b200(args):
         h_iq.copy_(iq[:, :e2e_nb * info.block_size])
         torch.cuda.synchronize()
 
-        # what the host link gives this rank while every rank copies at once: plain pinned H2D of the same
-        # buffer (into the resident copy: same bytes), CUDA-event timed
-        link = []
+        # what the host link gives all ranks together while every rank copies at once: a plain pinned H2D of the same
+        # buffer (into the resident copy: same bytes), CUDA-event timed per rank, started behind a barrier; the
+        # aggregate is all bytes over the SLOWEST rank's time (summing per-rank rates would flatter it: the ranks
+        # that finish first leave their share to the others)
+        link_total = 0.0
         for _ in range(2):
             barrier()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -441,11 +443,10 @@ def main_b200(args):
             iq[:, :e2e_nb * info.block_size].copy_(h_iq, non_blocking=True)
             a1.record(stream)
             torch.cuda.synchronize()
-            link.append(h_iq.numel() / (a0.elapsed_time(a1) * 1e-3) / 1e9)
-        t_l = torch.tensor([max(link)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_l, op=dist.ReduceOp.SUM)
-        link_total = float(t_l.item())
+            t_l = torch.tensor([a0.elapsed_time(a1) * 1e-3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_l, op=dist.ReduceOp.MAX)
+            link_total = max(link_total, world * h_iq.numel() / float(t_l.item()) / 1e9)
 
         def step_host():
             pipe.reset()

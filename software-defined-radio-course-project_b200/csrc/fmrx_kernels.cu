@@ -1162,6 +1162,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     float pred_integ = 0.0f, pred_ph = 0.0f;          // the predictor's state (warp 9)
 #ifdef FMRX_PLL_PROFILE
     long long prof_steps_cyc = 0, prof_wait = 0, prof_pre = 0, prof_one_cyc = 0;
+    long long prof_t_end = 0, prof_bar2 = 0, prof_hdr = 0, prof_bar1 = 0, prof_post = 0;    // warp 0: where a group's time outside its steps goes
     const long long prof_k0 = clock64();
     int prof_steps = 0, prof_n_stamp = 0, prof_n_c = 0, prof_n_fe = 0, prof_n_fm = 0;
     int prof_n_tie = 0, prof_n_range = 0, prof_n_inv = 0;
@@ -1197,6 +1198,11 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         const int cnt = min(PLL_GROUP, n - base);
         Chain ck;
         // ---- group header (warp 0) ----
+#ifdef FMRX_PLL_PROFILE
+        const long long prof_h0 = clock64();
+        if (warp == 0 && prof_t_end)
+            prof_bar2 += prof_h0 - prof_t_end;
+#endif
         if (warp == 0) {
             ck = ch;
             const bool again = s_redo != 0;          // (uniform: written before the barrier that ended the last pass)
@@ -1262,7 +1268,16 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 s_prog = base;
             }
         }
+#ifdef FMRX_PLL_PROFILE
+        const long long prof_h1 = clock64();
+#endif
         __syncthreads();
+#ifdef FMRX_PLL_PROFILE
+        if (warp == 0) {
+            prof_hdr += prof_h1 - prof_h0;
+            prof_bar1 += clock64() - prof_h1;
+        }
+#endif
         const int scheme = s_flag[0];
         const bool spec = scheme == 3;
         const bool again = s_flag[4] != 0;
@@ -1484,6 +1499,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 s_ulp_hist[g & 1] = ulp;
                 s_redo = redo;
             }
+#ifdef FMRX_PLL_PROFILE
+            prof_t_end = clock64();
+#endif
         } else if (role >= 2) {
             // ================= candidate tables =================
             if (scheme == 3) {
@@ -1866,6 +1884,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                    n_groups, n_exact, prof_n_stamp, prof_n_c, n_redone, prof_n_fe, prof_n_fm, prof_steps ? (double)prof_steps_cyc / prof_steps : 0.0, prof_steps, (double)(clock64() - prof_k0) / n,
                    (double)prof_pre / n_groups, (double)prof_wait / n_groups, (double)prof_steps_cyc / n_groups,
                    (double)(clock64() - prof_k0 - prof_pre - prof_wait - prof_steps_cyc) / n_groups);
+        if (c == 0)
+            printf("pll dbg group overhead (cycles per group, warp 0): waiting at the end-of-group barrier %.0f, header %.0f, waiting at the header barrier %.0f\n",
+                   (double)prof_bar2 / n_groups, (double)prof_hdr / n_groups, (double)prof_bar1 / n_groups);
         if (c == 0)
             printf("pll dbg one-hypothesis: groups %d (cut short %d), %.1f cyc/step over %d steps, exact blocks %d | groups without tables %d | predictor: %.1f cyc/step stepping, %.1f waiting for warp 0, %lld blocks of 8 reduced | candidate warp 2: %lld passes, %.0f cyc each, %.0f waiting for records\n",
                    prof_one_groups, prof_one_short, prof_one_steps ? (double)prof_one_cyc / prof_one_steps : 0.0, prof_one_steps, prof_one_exact, prof_checked,
