@@ -167,6 +167,19 @@ template <class T> FMRX_HD void rotate_quadrant(int n, T sn_r, T cs_r, T &sn, T 
     cs = ((q + 1) & 2) ? -b : b;
 }
 
+// low word of (nd + 1.5 * 2^52) for an integer-valued double |nd| < 2^31: nd as an int, without a conversion instruction
+FMRX_HD int quadrant_of(double nd)
+{
+    const double q = p_add(nd, FMRX_RINT_MAGIC);
+#if defined(__CUDACC__)
+    return __double2loint(q);
+#else
+    uint64_t u;
+    memcpy(&u, &q, sizeof(u));
+    return (int)(uint32_t)u;
+#endif
+}
+
 // cos of a float, rounded to float, for the NCO output (src/filter.cpp:170): same
 // reduction; arguments beyond its range take the library cos.
 FMRX_HD float cos_of_float(float a)
@@ -175,7 +188,9 @@ FMRX_HD float cos_of_float(float a)
         double sn_r, cs_r, r, nd, sn, cs;
         const TrigK K = trig_constants();
         sincos_reduced(K, (double)a, sn_r, cs_r, r, nd);
-        rotate_quadrant((int)nd, sn_r, cs_r, sn, cs);
+        // the quadrant count from the low word of nd + magic (an exact sum: nd is an integer below 2^24) instead of a
+        // double->int conversion: k_audio evaluates this once per IF sample and its conversion pipe is what is full
+        rotate_quadrant(quadrant_of(nd), sn_r, cs_r, sn, cs);
         return p_d2f(cs);
     }
     return p_d2f(cos((double)a));
