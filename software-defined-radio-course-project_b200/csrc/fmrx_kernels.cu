@@ -462,6 +462,7 @@ constexpr int PLL_PH_RING = 512;         // predicted-phaseEst records in flight
 constexpr int PLL_TABLES1 = 256;         // one-hypothesis rows in flight (16 bytes each: the same shared memory as the tables)
 constexpr int PLL_BATCH1 = 32;           // ... steps per pass of a candidate warp there: one per lane
 constexpr int PLL_LEAD1 = 256;           // ... and how far its predictor may run ahead of warp 0
+constexpr int PLL_PBLK = 16;             // ... steps per block of its predictor (one flow-control look, one |angle| test, one publication)
 constexpr int PLL_EXACT_MAX1 = 16;       // exact blocks after which a one-hypothesis group is finished without tables
 constexpr int PLL_HEAD = 48;             // steps of the NEXT group the predictor and the candidate warps do at the end of a group,
                                          // so that warp 0 finds its first tables waiting (multiple of 16)
@@ -1737,13 +1738,13 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 const bool short_form = onehyp_short_ok(s_hdr_tad, s_hdr[1]);   // trigArg small, phaseEst's grid coarse: the six-operation step
 
                 int prog = base;             // warp 0's progress as last seen: a block old (the load is issued a block ahead, its latency off this warp's path)
-                for (int t = 0; t < cnt; t += 8) {
+                for (int t = 0; t < cnt; t += PLL_PBLK) {
                     const int u0 = base + t;
                     int spin = 0;                // stay within PLL_LEAD1 of warp 0
 #ifdef FMRX_PLL_PROFILE
                     const long long pw0 = clock64();
 #endif
-                    while (prog != PLL_ABANDONED && u0 - prog > PLL_LEAD1 - 8 && ++spin < PLL_SPIN_LIMIT)
+                    while (prog != PLL_ABANDONED && u0 - prog > PLL_LEAD1 - PLL_PBLK && ++spin < PLL_SPIN_LIMIT)
                         asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(prog) : "r"(prog_a) : "memory");
 #ifdef FMRX_PLL_PROFILE
                     const long long pw1 = clock64();
@@ -1758,45 +1759,45 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     const unsigned ph_a0 = ph_a + (unsigned)(u0 & (PLL_PH_RING - 1)) * 8u;
                     // (loading the NEXT block's inputs here, under this block's steps, was tried: 5 % slower -- the 32 more
                     // live registers cost the schedule more than the exposed LDS latency)
-                    OneHypIn hs[8];
+                    OneHypIn hs[PLL_PBLK];
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
+                    for (int j = 0; j < PLL_PBLK; j++)
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                      : "=f"(hs[j].P), "=f"(hs[j].r), "=f"(hs[j].B), "=f"(hs[j].c)
                                      : "r"(h_a0 + (unsigned)j * (unsigned)sizeof(PllIn)));
-                    // eight steps without the angle reduction; if an angle left [-pi, pi] (P lost track of phaseEst by
-                    // whole turns, or a loop far from lock), the eight again with it -- and straight away for the next
-                    // blocks, trying the short step again every sixteenth block.  (Steps past the end of a short last
+                    // a block of steps without the angle reduction; if an angle left [-pi, pi] (P lost track of phaseEst by
+                    // whole turns, or a loop far from lock), the block again with it -- and straight away for the next
+                    // blocks, trying the unreduced step again every eighth block.  (Steps past the end of a short last
                     // group are never used.)
                     const float ang0 = ang, integ0 = integ, ph0 = ph;
-                    float phs[8];
+                    float phs[PLL_PBLK];
                     bool reduce = careful > 0;
                     if (!reduce) {
                         float amax = fabsf(ang);
                         if (short_form) {
-                            float crs[8];
+                            float crs[PLL_PBLK];
 #pragma unroll
-                            for (int j = 0; j < 8; j++)
+                            for (int j = 0; j < PLL_PBLK; j++)
                                 crs[j] = p_faddf(hs[j].c, -hs[j].r);
 #pragma unroll
-                            for (int j = 0; j < 8; j++) {
+                            for (int j = 0; j < PLL_PBLK; j++) {
                                 ang = onehyp_predictor_step_short(k, hs[j].P, crs[j], ang, integ, ph);
                                 phs[j] = ph;
-                                if (j < 7)
+                                if (j < PLL_PBLK - 1)
                                     amax = fmaxf(amax, fabsf(ang));
                             }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 8; j++) {
+                            for (int j = 0; j < PLL_PBLK; j++) {
                                 ang = onehyp_predictor_step(k, hs[j], ang, integ, ph);
                                 phs[j] = ph;
-                                if (j < 7)
+                                if (j < PLL_PBLK - 1)
                                     amax = fmaxf(amax, fabsf(ang));
                             }
                         }
                         reduce = !(amax <= FMRX_ONEHYP_PI);
                         if (reduce)
-                            careful = 16;
+                            careful = 8;
                     } else {
                         careful--;
                     }
@@ -1807,13 +1808,13 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                         if (!(fabsf(ang) <= FMRX_ONEHYP_PI))
                             ang = p_faddf(ang, -p_fmulf(6.2831855f, p_faddf(p_faddf(p_fmulf(ang, 0.15915494f), 12582912.0f), -12582912.0f)));
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
+                        for (int j = 0; j < PLL_PBLK; j++) {
                             ang = onehyp_predictor_step_reduced(k, hs[j], ang, integ, ph);
                             phs[j] = ph;
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
+                    for (int j = 0; j < PLL_PBLK; j++)
                         asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(ph_a0 + (unsigned)j * 8u), "r"(__float_as_int(phs[j])),
                                      "r"(u0 + j + 1)
                                      : "memory");

@@ -533,7 +533,7 @@ extern "C" int pll_model_onehyp_float(const float *pilot, int n, float freq, flo
     memset(&c, 0, sizeof(c));
     c.integ = state5[0]; c.ph = state5[1]; c.fi = state5[2]; c.fq = state5[3]; c.toff = state5[4];
     chain_load(c, k);
-    const int GROUP = 1024;
+    const int GROUP = 1024, PBLK = 16;
     static float pph[GROUP];
     static OneHypIn in1[GROUP];
     static double v[GROUP];
@@ -567,14 +567,14 @@ extern "C" int pll_model_onehyp_float(const float *pilot, int n, float freq, flo
             if (short_form && g < (1 << 17))
                 pll_model_grp_fail[g] |= 2;                        // (bit 1: the group ran the short predictor step)
             float a = onehyp_first_angle(pilot[base], c.tad);      // the angle from the exact trigArg before the group
-            for (int j0 = 0; j0 < cnt; j0 += 8) {          // as the predictor warp: blocks of 8, again with the reduction if an angle left [-pi, pi]
+            for (int j0 = 0; j0 < cnt; j0 += PBLK) {       // as the predictor warp: blocks of PBLK = 16 (PLL_PBLK), again with the reduction if an angle left [-pi, pi]
                 const float a0 = a, i0 = pi_, p0 = pp;
                 float amax = fabsf(a);
-                for (int j = j0; j < j0 + 8 && j < cnt; j++) {
+                for (int j = j0; j < j0 + PBLK && j < cnt; j++) {
                     a = short_form ? onehyp_predictor_step_short(k, in1[j].P, in1[j].c + -in1[j].r, a, pi_, pp)
                                    : onehyp_predictor_step(k, in1[j], a, pi_, pp);
                     pph[j] = pp;
-                    if (j + 1 < j0 + 8)
+                    if (j + 1 < j0 + PBLK)
                         amax = fmaxf(amax, fabsf(a));
                 }
                 if (!(amax <= FMRX_ONEHYP_PI)) {
@@ -582,7 +582,7 @@ extern "C" int pll_model_onehyp_float(const float *pilot, int n, float freq, flo
                     a = a0; pi_ = i0; pp = p0;
                     if (!(fabsf(a) <= FMRX_ONEHYP_PI))
                         a = a - 6.2831855f * ((a * 0.15915494f + 12582912.0f) - 12582912.0f);
-                    for (int j = j0; j < j0 + 8 && j < cnt; j++) {
+                    for (int j = j0; j < j0 + PBLK && j < cnt; j++) {
                         a = onehyp_predictor_step_reduced(k, in1[j], a, pi_, pp);
                         pph[j] = pp;
                     }

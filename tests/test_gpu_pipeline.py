@@ -33,6 +33,23 @@ def test_all_stages_bitwise(fm, port, synth, mode, taps, nblocks, chunk):
     assert np.array_equal(gpcm[0], opcm)
 
 
+@pytest.mark.parametrize("mode,taps,nblocks", [(0, 7, 5), (0, 29, 5), (0, 30, 5), (0, 31, 5), (0, 60, 5), (0, 61, 5), (0, 151, 6), (0, 256, 5),
+                                               (0, 512, 5), (1, 13, 5), (1, 200, 4), (3, 37, 1), (2, 64, 2)])
+def test_unusual_tap_counts(fm, port, synth, mode, taps, nblocks):
+    """`project --taps N` takes any N in 7..512.  The FIR kernels pad their tap loops (K1 to a multiple of 3*decim,
+    K2 to a multiple of 12) and size their windows and halos from N: counts at, just below and just above the
+    padding periods, tiny and maximal, for every decimation the modes have."""
+    info = port.mode(mode, taps)
+    iq = _capture(synth, info, nblocks, seed=taps)
+    stages = ("demod", "chan", "pilot", "trig", "mixer", "mono", "stereo")
+    opcm, od = port.chain(mode, taps).run(iq, stages)
+    with fm.Pipeline(mode, taps, 1, chunk_blocks=2, keep_stages=True) as p:
+        gpcm, gd = p.process_stages(iq, stages)
+    for s_ in stages:
+        assert_bits_equal(gd[s_][0], od[s_], f"mode {mode} taps {taps} stage {s_}")
+    assert np.array_equal(gpcm[0], opcm)
+
+
 def test_partial_trailing_block_is_dropped(fm, port, synth):
     info = port.mode(0, 51)
     iq = _capture(synth, info, 6, seed=2, extra=1234)
