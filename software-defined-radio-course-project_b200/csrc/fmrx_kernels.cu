@@ -437,7 +437,7 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 //            (pll_group_checked); after a failure speculation is retried with back-off.
 //   warps 1,5   I/O.  One lane per sample: the coalesced pilot load, (double)x, the IEEE
 //            reciprocal 1/x, the half-turn flag, w*trigOffset and its split on the float grid,
-//            the predictor's constant, for the group after next into a 4-group ring in shared
+//            the predictor's constant, for the next group into a 2-group ring in shared
 //            memory; and the coalesced store of the previous group's trigArg.
 //   (warps 4, 8 share warp 0's scheduler and only take part in the barriers.)
 //
@@ -454,8 +454,9 @@ constexpr int PLL_BATCH = 8;             // steps per pass of a candidate warp
 constexpr float PLL_ROW_INVALID = 0x1p100f;   // lq of a table nothing matches
 constexpr int PLL_IO_WARPS = 2;          // warps 1, 5 (scheduler 1); warps 4 and 8 (warp 0's scheduler) only take part in the barriers
 constexpr int PLL_PRED_WARP = 9;         // the run-ahead predictor (scheduler 1)
-constexpr int PLL_GROUP = 1024;          // steps between checkpoints / barriers
-constexpr int PLL_RING = 4 * PLL_GROUP;  // per-sample input ring: 4 groups
+constexpr int PLL_GROUP = 2048;          // steps between checkpoints / barriers (a group's header, its two barriers and the hand-over
+                                         // are ~3 500 cycles of cold serial code on warp 0: the longer the group the better)
+constexpr int PLL_RING = 2 * PLL_GROUP;  // per-sample input ring: the group running and the next one
 constexpr int kPllSpareSms = 32;         // SMs that must stay free for the FIR kernels before PLL CTAs claim whole SMs
 constexpr int PLL_TABLES = 128;          // candidate tables in flight (a ring over the steps)
 constexpr int PLL_PH_RING = 512;         // predicted-phaseEst records in flight
@@ -550,6 +551,7 @@ struct TableRun {
     int base, cnt;                   // first step and number of steps of the group
     unsigned in_base, tab_base, sg_base, prog_addr;   // shared-window addresses: ring {vi, vr}, tables, parked indices, progress word
     unsigned sph_base, kb_base;      // ... the predictor's records, the per-block kbase of the group (for the I/O warp)
+    unsigned head_addr;              // ... the I/O warps' words about the head of the next group (pll_block_exact)
     int cont;                        // the group continues the one before: pi of its first block comes from the predictor too
 #ifdef FMRX_PLL_PROFILE
     int prof_stamp, prof_c, prof_fatal_exact;
@@ -557,7 +559,9 @@ struct TableRun {
 #endif
     int gi;                          // in: grid index of the trigArg before the group; out: of the last one
     int n_exact;                     // out: blocks of 16 that had to be stepped the exact way
-    int fatal;                       // out: a block could not be completed here; the caller redoes the group
+    int fatal;                       // out: the group was not completed here: 1 too many exact blocks (the caller redoes the group),
+                                     // 2 an exact block left the group's grid (the caller finishes it without tables, from t_stop)
+    int t_stop;                      // out: steps of the group completed when it stopped
     // for the exact steps
     const PllIn *ring;               // the per-sample input ring
     pllcore::Consts k;
@@ -606,7 +610,19 @@ __device__ __noinline__ bool pll_block_exact(TableRun &r, int u0, int nsteps, co
     }
     if (c.binade == FMRX_DISARMED || c.ulp != r.ulp)
         return false;
-    // Kp*errorD, Ki*errorD of the sample after the block, from the now known trigArg
+    // Kp*errorD, Ki*errorD of the sample after the block, from the now known trigArg (the first sample of the next
+    // group, at the very end of this one: the I/O warps say when that one is in the ring)
+    if (u0 + nsteps == r.base + PLL_GROUP) {
+        int a0 = 0, a1 = 0;
+        for (int spin = 0; spin < PLL_SPIN_LIMIT; spin++) {
+            asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(a0) : "r"(r.head_addr) : "memory");
+            asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(a1) : "r"(r.head_addr + 4u) : "memory");
+            if (a0 == u0 + nsteps && a1 == u0 + nsteps)
+                break;
+        }
+        if (a0 != u0 + nsteps || a1 != u0 + nsteps)
+            return false;
+    }
     const PllIn nx = r.ring[(u0 + nsteps) & (PLL_RING - 1)];
     const Feedback f = make_feedback(K, c.tad, pll_turn(nx.x), nx.inv_x, nullptr, nullptr);
     bool ok = true;
@@ -973,7 +989,7 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
         bad |= (int)!have;
     };
     int t = 0;
-    bool fatal = false;
+    int fatal = 0;               // 1: too many exact blocks; 2: an exact block left the group's grid (r.integ, r.ph, r.gi: the state before it)
     const int n_full = cnt >> 4;
     if (r.cont) {        // (once per group: this one may wait for the load)
         const int2 rec = load_rec(base - 1);
@@ -1035,8 +1051,12 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
         // its store and skips it if warp 0 has left its batch behind, and warp 0 cannot cover the 120 steps from
         // there to this row in the few cycles between that look and the store.  Reading the 16 stamps once more
         // here instead cost 7 cycles per step: the dependent LDS + vote sits on the block's critical path.)
-        if (!settle(u0, 16, integ0, ph0, gi0) || n_exact > PLL_EXACT_MAX) {
-            fatal = true;            // (more exact blocks than a group without tables costs: give the group up)
+        if (!settle(u0, 16, integ0, ph0, gi0)) {
+            fatal = 2;
+            break;
+        }
+        if (n_exact > PLL_EXACT_MAX) {
+            fatal = 1;               // (more exact blocks than a group without tables costs: give the group up)
             break;
         }
         // progress: lets the candidate warps reuse the table rows of this block, the predictor run on
@@ -1059,15 +1079,18 @@ __device__ __noinline__ void pll_table_group(TableRun &r, const int lane)
             gi = vg.x + kbase + __float_as_int(p_faddf(p_faddf(__int_as_float(tb), __int_as_float(vg.y)), 12582912.0f));
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(sg_base + 4u * (unsigned)(t + j)), "r"(tb) : "memory");
         }
-        fatal = !settle(u0, nb, integ0, ph0, gi0);
+        fatal = settle(u0, nb, integ0, ph0, gi0) ? 0 : 2;
     }
     r.fatal = fatal;
+    r.t_stop = t;
+    r.n_exact = n_exact;
+    if (fatal == 2)              // (r.integ, r.ph, r.gi: the state before the block that could not be done, as settle() left them)
+        return;
     r.integ = integ;
     r.ph = ph;
     r.kpe = kpe;
     r.kie = kie;
     r.gi = gi;
-    r.n_exact = n_exact;
 }
 
 __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
@@ -1085,11 +1108,14 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     __shared__ PllRow s_tab[PLL_TABLES];              // candidate tables, a ring over the steps (one-hypothesis groups: PLL_TABLES1 rows of 16 bytes)
     __shared__ __align__(16) int s_g[2][PLL_GROUP];                 // what warp 0 parks per step of the group (see s_spec), double-buffered
     __shared__ double s_grid[2];                      // ulp, 1/ulp of the current group
-    __shared__ double s_prep_ulp[4];                  // ulp the ring slots of each group were prepared with
+    __shared__ double s_prep_ulp[2];                  // ulp the ring slots of each group were prepared with
+    __shared__ int s_head_ready[PLL_IO_WARPS];        // I/O warp w has prepared its share of the first 64 samples of the group starting HERE
+                                                      // (the rest of that group is only touched behind the barrier that ends this one)
     __shared__ double s_ulp_hist[2];                  // ulp the parked grid indices of a group refer to
     __shared__ int s_spec[2];                         // what s_g holds: 0 float trigArg, 1 the bits of t (three-hypothesis steps), 2 the bits of phaseEst
+    __shared__ int s_split[2];                        // ... kind 1: only the first s_split steps; float trigArg from there on
     __shared__ int s_flag[5];                         // [0] scheme of the group: 0 none, 3 three hypotheses, 1 one hypothesis; [1] error;
-                                                      // [2] the next group's slots are stale; [3] the group continues the one before (its head
+                                                      // [2] re-grid the group's ring slot first (binade change); [3] the group continues the one before (its head
                                                       // is already done); [4] this pass repeats the group of the pass before (its tables failed)
     __shared__ int s_redo;                            // warp 0, at the end of a pass: do this group again (on the one-hypothesis scheme)
 
@@ -1117,9 +1143,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
 
     // I/O warp: one lane per sample, off-chain inputs of the samples of a group into the ring.  The one-hypothesis
     // inputs extrapolate phaseEst from e_ph, its value before step e_base, with e_slope per step.
-    auto prepare = [&](int base, float e_slope, float e_ph, int e_base) {
-        for (int j = 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS) {
-            const int u = base + j + lane;
+    auto prepare_one = [&](int u, float e_slope, float e_ph, int e_base) {
+        {
             const float pvv = (u < n) ? p[u] : 1.0f;
             const float pnx = (u + 1 < n) ? p[u + 1] : 1.0f;
             PllIn in;
@@ -1135,8 +1160,24 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             in.h1 = onehyp_inputs(in.v, e_ph, e_slope, u + 1 - e_base, pnx);
             s_in[u & (PLL_RING - 1)] = in;
         }
+    };
+    auto prepare = [&](int base, float e_slope, float e_ph, int e_base) {
+        for (int j = 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS)
+            prepare_one(base + j + lane, e_slope, e_ph, e_base);
         if (lane == 0 && io_id == 0)
-            s_prep_ulp[(base / PLL_GROUP) & 3] = s_grid[0];
+            s_prep_ulp[(base / PLL_GROUP) & 1] = s_grid[0];
+    };
+    // the first samples of the NEXT group are read before the barrier that ends this one (by the predictor and the
+    // candidate warps doing its head, by an exact block at the very end of this group): wait for the I/O warps' word
+    auto head_ready = [&](int next_base) -> bool {
+        for (int spin = 0; spin < PLL_SPIN_LIMIT; spin++) {
+            int a0, a1;
+            asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(a0) : "r"(smem_u32(&s_head_ready[0])) : "memory");
+            asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(a1) : "r"(smem_u32(&s_head_ready[1])) : "memory");
+            if (a0 == next_base && a1 == next_base)
+                return true;
+        }
+        return false;
     };
 
     for (int i = threadIdx.x; i < PLL_PH_RING; i += PLL_THREADS)
@@ -1149,6 +1190,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     if (threadIdx.x == 0) {
         s_flag[1] = 0;
         s_redo = 0;
+        s_head_ready[0] = s_head_ready[1] = -1;
     }
     // warp 0 owns the recurrence state
     Chain ch;
@@ -1163,7 +1205,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     float pred_integ = 0.0f, pred_ph = 0.0f;          // the predictor's state (warp 9)
 #ifdef FMRX_PLL_PROFILE
     long long prof_steps_cyc = 0, prof_wait = 0, prof_pre = 0, prof_one_cyc = 0;
-    long long prof_t_end = 0, prof_bar2 = 0, prof_hdr = 0, prof_bar1 = 0, prof_post = 0;    // warp 0: where a group's time outside its steps goes
+    long long prof_t_end = 0, prof_bar2 = 0, prof_hdr = 0, prof_bar1 = 0, prof_post = 0, prof_post2 = 0, prof_c1 = 0;    // warp 0: where a group's time outside its steps goes
     const long long prof_k0 = clock64();
     int prof_steps = 0, prof_n_stamp = 0, prof_n_c = 0, prof_n_fe = 0, prof_n_fm = 0;
     int prof_n_tie = 0, prof_n_range = 0, prof_n_inv = 0;
@@ -1191,7 +1233,6 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     __syncthreads();
     if (role == 1 && io_id < PLL_IO_WARPS) {
         prepare(0, st[0], st[1], 0);
-        prepare(PLL_GROUP, st[0], st[1], 0);
     }
     __syncthreads();
 
@@ -1218,13 +1259,18 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             // (Tables also serve the regime past trigOffset == 2^24, where trigArg freezes on two grid points
             // and the loop dithers across a float rounding boundary: tests/test_gpu_operators.py::
             // test_pll_long_run_past_counter_saturation and the >= 70 s pipeline runs of tests/test_gpu_long_runs.py.)
-            const bool can3 = usable && !again && skip == 0 && s_prep_ulp[g & 3] == ch.ulp &&
-                              (double)fabsf(ch.ph) < ch.ulp * 16777216.0;
+            const bool can3 = usable && !again && skip == 0 && (double)fabsf(ch.ph) < ch.ulp * 16777216.0;
+            // the group's ring slot was prepared while the group before ran, with ITS grid: after a binade change
+            // (vi, vr) are re-made for the new one before anything else happens (below, all warps)
+            const bool regrid = can3 && s_prep_ulp[g & 1] != ch.ulp;
             const int scheme = can3 ? 3 : usable ? 1 : 0;
             // the group before ran on tables to its end and hardly needed the exact step: predictor and
             // candidates did our head, and the predictor carries on from its own state (otherwise it
             // restarts from the exact one: it may have drifted)
-            const bool cont = scheme == 3 && prev_scheme == 3 && have_ed && prev_exact <= 2;
+            const bool cont = scheme == 3 && prev_scheme == 3 && have_ed && prev_exact <= 2 && !regrid;
+#ifdef FMRX_PLL_PROFILE
+            prof_post += clock64() - prof_h0;        // (header, first part: copy and decisions)
+#endif
             if (scheme != prev_scheme || again) {
                 // the other scheme's rows (and records) share the rings: nothing of them may be taken for this group's
                 for (int i = lane; i < PLL_TABLES; i += 32) {
@@ -1250,9 +1296,9 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             }
             if (lane == 0) {
                 s_flag[0] = scheme;
+                s_flag[2] = regrid;
                 s_grid[0] = ch.ulp;
                 s_grid[1] = ch.inv_ulp;
-                s_flag[2] = ch.binade != FMRX_DISARMED && s_prep_ulp[(g + 1) & 3] != ch.ulp;
                 s_flag[3] = cont;
                 s_flag[4] = again;
                 s_kbase = __float_as_int(p_faddf(p_fmulf(ch.ph, (float)ch.inv_ulp), 12582912.0f)) - 0x4B400000 - 0x4B400000;
@@ -1279,6 +1325,18 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
             prof_bar1 += clock64() - prof_h1;
         }
 #endif
+        if (s_flag[2]) {         // (uniform)
+            const double iu = s_grid[1];
+            for (int j = threadIdx.x; j < PLL_GROUP; j += PLL_THREADS) {
+                PllIn &in = s_in[(base + j) & (PLL_RING - 1)];
+                const double qv = grid_round(in.v, iu);
+                in.vi = grid_index(qv);
+                in.vr = __double2float_rn(__fma_rn(in.v, iu, -p_add(qv, -FMRX_RINT_MAGIC)));
+            }
+            if (threadIdx.x == 0)
+                s_prep_ulp[g & 1] = s_grid[0];
+            __syncthreads();
+        }
         const int scheme = s_flag[0];
         const bool spec = scheme == 3;
         const bool again = s_flag[4] != 0;
@@ -1295,6 +1353,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 n_groups++;
             bool good = scheme != 0;
             bool redo = false;
+            bool regridded = false;  // a table group that ended without tables after a binade change
+            int split = 0;           // three-hypothesis groups: steps parked as bits of t; the rest (after a binade change) as float trigArg
             int parked = 0;          // what s_g holds at the end (s_spec)
             if (scheme == 3) {
                 float integ = ch.integ, ph = ch.ph;
@@ -1360,6 +1420,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 r.prog_addr = smem_u32(&s_prog);
                 r.sph_base = smem_u32(&s_ph[0]);
                 r.kb_base = smem_u32(&s_kb_blk[g & 1][0]);
+                r.head_addr = smem_u32(&s_head_ready[0]);
                 r.cont = s_flag[3];
 #ifdef FMRX_PLL_PROFILE
                 r.prof_stamp = r.prof_c = r.prof_fatal_exact = 0;
@@ -1379,7 +1440,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
 #endif
                     pll_table_group(r, lane);
 #ifdef FMRX_PLL_PROFILE
-                    prof_steps_cyc += clock64() - prof_c0;
+                    prof_c1 = clock64();
+                    prof_steps_cyc += prof_c1 - prof_c0;
                     prof_steps += cnt;
                     prof_n_stamp += r.prof_stamp;
                     prof_n_c += r.prof_c;
@@ -1393,7 +1455,23 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     n_exact += r.n_exact;
                     prev_exact = r.n_exact;
                 }
-                if (good) {
+                if (good && r.fatal == 0)
+                    split = cnt;
+                if (r.fatal == 2) {
+                    // trigArg left the binade the group's grid belongs to (in mode 0 it grows with w*trigOffset: some
+                    // twenty times per capture, most of them in its first seconds).  The blocks before are done and
+                    // parked; the rest of the group goes without tables from the state before the block at hand --
+                    // no second pass -- and the next group starts afresh on the new grid (its ring slot is
+                    // re-gridded in its header pass).
+                    asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(smem_u32(&s_prog)), "r"(PLL_ABANDONED) : "memory");
+                    split = r.t_stop;
+                    onehyp_chain_at(ch, r.integ, r.ph, (float)min(t0 + base + r.t_stop, 16777216), p_mul((double)r.gi, ulp));
+                    pll_group_checked(ch, k, s_in, base, r.t_stop, cnt, regular, smem_u32(&s_g[g & 1][0]), false);
+                    stale = false;
+                    have_ed = false;
+                    parked = 1;
+                    regridded = true;        // (prev_scheme = 0 below: nothing of this group's head work is taken over)
+                } else if (good) {
                     ch.integ = r.integ;
                     ch.ph = r.ph;
                     ch.toff = (float)min(t0 + base + cnt, 16777216);
@@ -1409,7 +1487,7 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                     // one-hypothesis scheme, and the tables rest for a while
                     asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(smem_u32(&s_prog)), "r"(PLL_ABANDONED) : "memory");
                     n_redone++;
-                    backoff = min(backoff ? 2 * backoff : 1, PLL_BACKOFF_MAX);
+                    backoff = min(backoff < 4 ? backoff + 1 : 2 * backoff, PLL_BACKOFF_MAX);       // 1, 2, 3, 4, 8, 16, ...
                     skip = backoff;
                     ch = ck;
                     have_ed = false;
@@ -1494,14 +1572,18 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 have_ed = false;
                 parked = 0;
             }
-            prev_scheme = redo ? 0 : scheme;
+            prev_scheme = redo || regridded ? 0 : scheme;
             if (lane == 0) {
                 s_spec[g & 1] = parked;
+                s_split[g & 1] = split;
                 s_ulp_hist[g & 1] = ulp;
                 s_redo = redo;
             }
 #ifdef FMRX_PLL_PROFILE
             prof_t_end = clock64();
+            if (prof_c1)
+                prof_post2 += prof_t_end - prof_c1;
+            prof_c1 = 0;
 #endif
         } else if (role >= 2) {
             // ================= candidate tables =================
@@ -1522,8 +1604,16 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 const int first = base + (cont ? PLL_HEAD : 0);
                 const int end = base + cnt + (base + cnt + PLL_HEAD <= n ? PLL_HEAD : 0);
                 const int q0 = first / PLL_BATCH;
+                bool head_seen = false;
                 for (int ub8 = first + ((cand_id - q0 % PLL_CAND_WARPS + PLL_CAND_WARPS) % PLL_CAND_WARPS) * PLL_BATCH; ub8 < end;
                      ub8 += PLL_BATCH * PLL_CAND_WARPS) {
+                    if (!head_seen && cnt == PLL_GROUP && ub8 + PLL_BATCH >= base + cnt) {      // samples of the next group from here on
+                        if (!head_ready(base + PLL_GROUP)) {
+                            s_flag[1] = 1;
+                            break;
+                        }
+                        head_seen = true;
+                    }
                     const bool live = ub8 + sq < end;
                     const int u = ub8 + (live ? sq : 0);
                     const double v = s_in[u & (PLL_RING - 1)].v;
@@ -1701,6 +1791,10 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                 const int t_end = cnt + (base + cnt + PLL_HEAD <= n ? PLL_HEAD : 0);
                 for (int t = cont ? PLL_HEAD : 0; t < t_end; t += 16) {
                     const int u0 = base + t;
+                    if (t == PLL_GROUP && !head_ready(base + PLL_GROUP)) {      // the head of the next group starts here
+                        s_flag[1] = 1;
+                        break;
+                    }
                     int spin = 0;                // stay within PLL_PRED_LEAD of warp 0
                     do {
                         asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(prog) : "r"(prog_a) : "memory");
@@ -1830,22 +1924,32 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
         } else if (role == 1 && io_id < PLL_IO_WARPS) {
             // ================= I/O =================
             if (!again) {            // (a pass that repeats a group has nothing new to load or store)
-                // (a binade change strands the two groups prepared ahead with the old grid: the next one
-                // is prepared again here, so that only the group running now goes without tables)
-                if (s_flag[2])
-                    prepare(base + PLL_GROUP, s_hdr[2], s_hdr[1], base);
-                prepare(base + 2 * PLL_GROUP, s_hdr[2], s_hdr[1], base);
-                if (g > 0) {                     // previous group: always complete
-                    const int pb = base - PLL_GROUP, pg = (g - 1) & 1;
-                    const int kind = s_spec[pg];
-                    for (int j = lane + 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS) {
+                // Sample by sample: the trigArg of the group before (always complete) out of its ring slot, then the
+                // inputs of the NEXT group into the same slot (the ring holds two groups).  Prepared with the grid of
+                // the group running now: after a binade change only the group that was prepared with the old grid goes
+                // without tables.
+                const int pb = base - PLL_GROUP, pg = (g - 1) & 1;
+                const int kind_g = g > 0 ? s_spec[pg] : 0, split = g > 0 ? s_split[pg] : 0;
+                for (int j = lane + 32 * io_id; j < PLL_GROUP; j += 32 * PLL_IO_WARPS) {
+                    if (g > 0) {
                         const PllIn &in = s_in[(pb + j) & (PLL_RING - 1)];
                         const int w = s_g[pg][j];
+                        const int kind = kind_g == 1 && j >= split ? 0 : kind_g;
                         tr[pb + j] = kind == 1   ? __double2float_rn(p_mul((double)parked_index(w, in, s_kb_blk[pg][j >> 4]), s_ulp_hist[pg]))
                                      : kind == 2 ? __double2float_rn(onehyp_trigarg(in.v, __int_as_float(w)))
                                                  : __int_as_float(w);
                     }
+                    prepare_one(base + PLL_GROUP + j, s_hdr[2], s_hdr[1], base);
+                    if (j < 32 * PLL_IO_WARPS) {         // the head of the next group is there: say so (see head_ready)
+                        __syncwarp();
+                        if (lane == 0) {
+                            __threadfence_block();
+                            asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(smem_u32(&s_head_ready[io_id])), "r"(base + PLL_GROUP) : "memory");
+                        }
+                    }
                 }
+                if (lane == 0 && io_id == 0)
+                    s_prep_ulp[(g + 1) & 1] = s_grid[0];
             }
         }
         __syncthreads();
@@ -1857,10 +1961,11 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
     // the last group's trigArg
     if (warp == 1 && n > 0) {
         const int g = (n - 1) / PLL_GROUP, pb = g * PLL_GROUP, pg = g & 1;
-        const int kind = s_spec[pg];
+        const int kind_g = s_spec[pg], split = s_split[pg];
         for (int j = lane; pb + j < n && j < PLL_GROUP; j += 32) {
             const PllIn &in = s_in[(pb + j) & (PLL_RING - 1)];
             const int w = s_g[pg][j];
+            const int kind = kind_g == 1 && j >= split ? 0 : kind_g;
             tr[pb + j] = kind == 1   ? __double2float_rn(p_mul((double)parked_index(w, in, s_kb_blk[pg][j >> 4]), s_ulp_hist[pg]))
                          : kind == 2 ? __double2float_rn(onehyp_trigarg(in.v, __int_as_float(w)))
                                      : __int_as_float(w);
@@ -1886,8 +1991,8 @@ __global__ void __launch_bounds__(PLL_THREADS) k_pll(const PllArgs a)
                    (double)prof_pre / n_groups, (double)prof_wait / n_groups, (double)prof_steps_cyc / n_groups,
                    (double)(clock64() - prof_k0 - prof_pre - prof_wait - prof_steps_cyc) / n_groups);
         if (c == 0)
-            printf("pll dbg group overhead (cycles per group, warp 0): waiting at the end-of-group barrier %.0f, header %.0f, waiting at the header barrier %.0f\n",
-                   (double)prof_bar2 / n_groups, (double)prof_hdr / n_groups, (double)prof_bar1 / n_groups);
+            printf("pll dbg group overhead (cycles per group, warp 0): waiting at the end-of-group barrier %.0f, header %.0f (its decisions %.0f), waiting at the header barrier %.0f, after the table steps %.0f\n",
+                   (double)prof_bar2 / n_groups, (double)prof_hdr / n_groups, (double)prof_post / n_groups, (double)prof_bar1 / n_groups, (double)prof_post2 / n_groups);
         if (c == 0)
             printf("pll dbg one-hypothesis: groups %d (cut short %d), %.1f cyc/step over %d steps, exact blocks %d | groups without tables %d | predictor: %.1f cyc/step stepping, %.1f waiting for warp 0, %lld blocks of 8 reduced | candidate warp 2: %lld passes, %.0f cyc each, %.0f waiting for records\n",
                    prof_one_groups, prof_one_short, prof_one_steps ? (double)prof_one_cyc / prof_one_steps : 0.0, prof_one_steps, prof_one_exact, prof_checked,

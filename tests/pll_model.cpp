@@ -533,13 +533,13 @@ extern "C" int pll_model_onehyp_float(const float *pilot, int n, float freq, flo
     memset(&c, 0, sizeof(c));
     c.integ = state5[0]; c.ph = state5[1]; c.fi = state5[2]; c.fq = state5[3]; c.toff = state5[4];
     chain_load(c, k);
-    const int GROUP = 1024, PBLK = 16;
+    const int GROUP = 2048, PBLK = 16;       // PLL_GROUP, PLL_PBLK
     static float pph[GROUP];
     static OneHypIn in1[GROUP];
     static double v[GROUP];
     auto bits = [](float f) { int i; memcpy(&i, &f, 4); return i; };
-    // (integ, ph) at the start of every group: prepare() for group g extrapolates from the start of group g - 2
-    // (the I/O warps work two groups ahead; the launch's initial state for the first two groups)
+    // (integ, ph) at the start of every group: the inputs of group g are prepared while group g - 1 runs, and
+    // extrapolate from its start (the launch's initial state for the first two groups)
     static float h_slope[1 << 17], h_ph[1 << 17];
     for (int base = 0, g = 0; base < n; base += GROUP, g++) {
         const int cnt = n - base < GROUP ? n - base : GROUP;
@@ -551,7 +551,7 @@ extern "C" int pll_model_onehyp_float(const float *pilot, int n, float freq, flo
             h_slope[g] = g > 0 ? (c.ph + -h_ph[g - 1]) * (1.0f / GROUP) : c.integ;      // as k_pll's header: the slope over the group before
             h_ph[g] = c.ph;
         }
-        const int og = g >= 2 ? g - 2 : 0;
+        const int og = g >= 1 ? g - 1 : 0;
         const float e_integ = h_slope[og], e_ph = h_ph[og];
         const int e_age = (g - og) * GROUP;
         if (regular) {

@@ -105,7 +105,7 @@ def test_fast_pll_other_loop_parameters(model, port):
 def test_predictor_tracks_the_exact_recurrence(model, port, synth, mode, seed, pilot_hz):
     """k_pll centres each step's candidate table (16 grid points, [G-8, G+7]) on the run-ahead
     predictor's phaseEst (csrc/fmrx_pll_core.h predictor_step), restarted from the exact state
-    every 1024 steps.  On a locked loop the exact trigArg must stay within two grid steps of
+    at the latest every 2048 steps (PLL_GROUP).  On a locked loop the exact trigArg must stay within two grid steps of
     that centre for every group after the first (where trigArg starts at 0 and the float grid
     is arbitrarily fine)."""
     info = port.mode(mode, 51)
@@ -113,7 +113,7 @@ def test_predictor_tracks_the_exact_recurrence(model, port, synth, mode, seed, p
     iq = synth.synth_iq(nb * info.block_size // 2, info.rf_fs, seed=seed, pilot_hz=pilot_hz)
     _, st = port.chain(mode, 51).run(iq, stages=("pilot",))
     pilot = st["pilot"]
-    group = 1024
+    group = 2048
     worst = np.zeros((len(pilot) + group - 1) // group, np.int32)
     state = np.array([0.0, 0.0, 1.0, 0.0, 0.0], np.float32)
     model.pll_model_predict.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, f32p, C.c_int,
