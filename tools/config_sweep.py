@@ -40,7 +40,7 @@ def main():
     cases = [
         ("m0_t101_1x60s", "configs[0] mode 0 mono, 101 taps (the reference ignores `channels`: same R,L stream)", ["long_m0_t101_60s"]),
         ("m0_t51_1x80s", "configs[1] mode 0 stereo, 51 taps, one capture, across the counter's saturation (69.9 s)", ["long_m0_t51_80s"]),
-        ("m1_t51_1x65s", "mode 1 (1.44 Msps, decim 4), 51 taps, across saturation (58.3 s)", ["long_m1_t51_65s"]),
+        ("m1_t51_1x65s", "mode 1 (1.152 Msps, decim 4), 51 taps, across saturation (58.3 s)", ["long_m1_t51_65s"]),
         ("m2_t51_1x75s", "configs[2] mode 2 (147/800 polyphase to 44.1 kHz), 51 taps, across saturation (69.9 s)", ["long_m2_t51_75s"]),
         ("m3_t51_1x70s", "configs[2] mode 3 (2.304 Msps, 441/2560 polyphase), 51 taps, across saturation (65.5 s)", ["long_m3_t51_70s"]),
         ("m0_t301_1x25s", "mode 0, 301 taps, one capture", ["long_m0_t301_25s"]),
