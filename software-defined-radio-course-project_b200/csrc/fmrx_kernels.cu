@@ -412,8 +412,9 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 //   warp 9   the predictor.  The phase detector computes atan2(x*(-sin t), x*cos t), which
 //            up to float rounding is wrap(pi*(x < 0) - t): with that, a step of the recurrence
 //            is a handful of float operations (predictor_step), about half of what warp 0
-//            needs.  The predictor runs ahead of warp 0 (restarted from the exact state at
-//            every group of 1024 steps) and publishes its phaseEst of every step.  It is
+//            needs.  The predictor runs ahead of warp 0 (restarted from the exact state
+//            whenever a group of PLL_GROUP steps does not simply continue the one before)
+//            and publishes its phaseEst of every step.  It is
 //            never used for a result -- it says which float trigArg(u) will almost certainly
 //            be: on a locked loop the exact trigArg is the predicted float grid point or a
 //            neighbour (tests/test_pll_model.py::test_predictor_tracks_the_exact_recurrence).
@@ -432,9 +433,10 @@ cudaError_t launch_bandpass_pair(const BandpassArgs &a, int n_captures, cudaStre
 //            bound by instruction issue, not latency.  Guards only accumulate; a block of 16
 //            steps with a failed guard (table late or not this block's, grid point not among
 //            the three, a candidate's own guard, sum too close to a rounding tie) is stepped
-//            again the exact way (pll_block_exact), and a group that cannot be completed on
-//            its grid (binade change, too many exact blocks) is redone without tables
-//            (pll_group_checked); after a failure speculation is retried with back-off.
+//            again the exact way (pll_block_exact).  A group that needs too many of those is
+//            done again on the one-hypothesis scheme and the tables are retried with back-off;
+//            a group whose trigArg leaves the binade of its grid is finished without tables
+//            from the block at hand (pll_group_checked), no second pass.
 //   warps 1,5   I/O.  One lane per sample: the coalesced pilot load, (double)x, the IEEE
 //            reciprocal 1/x, the half-turn flag, w*trigOffset and its split on the float grid,
 //            the predictor's constant, for the next group into a 2-group ring in shared
